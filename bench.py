@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: V-cycles/sec at N=16384 fp64 (+ smoother HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--nmax 16384]
+
+One "step" = one V-cycle of the shipped Vcycle.txt shape (con_step=3, con_N=1, N_min=8,
+Gauss-Seidel 1e-7 at the coarsest grid) over the analytic source grid ("synthetic": generated
+by getSource, no dataset), run by the C++ cycle driver of libmgb200 through the C ABI.
+
+ value  whole-job V-cycles/s with the source grid already resident in HBM
+ e2e    the same V-cycle through mgRunCycleFileHost with HOST buffers: the source grid is copied
+        H2D from pinned memory and the solution D2H inside the timed region, every step
+ roofline      the dominant kernel timed alone with CUDA events on the library's stream
+ cpu_baseline  the unmodified reference operators (oracle/_ref) on the host cores, bounded sample
+
+--impl reference runs the reference's own CPU implementation (oracle/_ref operators driven by
+the oracle's restatement of main()) with all host threads on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "V-cycles/sec at N=16384 fp64"
+UNIT = "V-cycles/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def write_cycle(text):
+    f = tempfile.NamedTemporaryFile("w", suffix=".txt", prefix="cycle_", delete=False)
+    f.write(text)
+    f.close()
+    return f.name
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.path = gpu, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_run(sample_N, threads, repeats, nmax):
+    """Times V-cycles of the same shape at sample_N with the reference's own operators
+    (oracle/_ref/libmgref.so, built -O0 -fopenmp exactly as src/Makefile:8) when present, else
+    the oracle port.  Returns (kind, [seconds per cycle], mg_error)."""
+    from oracle import pyoracle as po
+    from multigrid_poisson_solver_b200 import cycles
+    path = write_cycle(cycles.v_cycle(sample_N, 8))
+    if po.have_ref():
+        kind, ops = "reference", po.ref_ops(threads)
+    else:
+        kind, ops = "port", None
+    times, err = [], None
+    for _ in range(repeats):
+        r = po.run_cycle(path, ops=ops, threads=threads, want_U=False)
+        times.append(r["time_ms"] / 1000.0)      # the reference's own timer span (:156,:429)
+        err = r["mg_error"]
+    os.unlink(path)
+    return kind, times, err
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample_N = args.ref_sample
+    kind, times, err = cpu_reference_run(sample_N, threads, args.warmup + args.steps, args.nmax)
+    timed = times[args.warmup:]
+    sec = sum(timed) / len(timed)
+    scale = (sample_N / args.nmax) ** 2           # DOF ratio: a V-cycle's work is linear in N^2
+    value = scale / sec
+    sample = ("V-cycle N_max=%d (same shape: 3+3 sweeps, N/2 ladder to 8, GS 1e-7) timed with the reference's own "
+              "timer span; V-cycles/s at N=%d obtained by the DOF ratio (%d/%d)^2" % (sample_N, args.nmax, sample_N, args.nmax))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sec / scale, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Vcycle.txt shape at N_max=%d N_min=8 step=3 (CPU sample at N_max=%d)" % (args.nmax, sample_N)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fine_dof_cycles_per_s": value * args.nmax ** 2, "sample_ms_per_cycle": 1000.0 * sec, "sample_mg_error": err,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nmax", type=int, default=16384)
+    ap.add_argument("--ref-sample", type=int, default=4096, help="N_max of the bounded CPU sample")
+    ap.add_argument("--unfused", action="store_true", help="one ABI operator per reference call")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import multigrid_poisson_solver_b200 as mg
+    from multigrid_poisson_solver_b200 import api, cycles
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = mg.init(local)
+    stream = torch.cuda.ExternalStream(lib.mgStream(), device=local)
+
+    def barrier():
+        lib.mgSync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N = args.nmax
+    n = N * N
+    path = write_cycle(cycles.v_cycle(N, 8))
+    base_flags = (mg.RUN_UNFUSED if args.unfused else mg.RUN_FUSED) | mg.RUN_QUIET | mg.RUN_NO_FINAL_ERROR
+    flags = base_flags | mg.RUN_SKIP_SOURCE
+
+    # ---- device-resident run -------------------------------------------------------------
+    F = mg.DeviceGrid(N)
+    lib.getSource(N, 1.0, F.ptr, 0.0, 0.0)
+    recs = (api.TraceRec * 64)()
+    res = api.CycleResult()
+
+    def one_cycle():
+        rc = lib.mgRunCycleFile(os.fsencode(path), flags, F.ptr, None, recs, 64, res)
+        if rc != 0:
+            raise SystemExit("mgRunCycleFile failed: %d %s" % (rc, lib.mgLastError().decode()))
+        return res.launches, res.time_ms
+
+    for _ in range(args.warmup):
+        one_cycle()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, inner_ms = 0, 0.0
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            l, t = one_cycle()
+            launches += l
+            inner_ms += t
+        ev1.record(stream)
+        barrier()
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = clk.summary()
+    ms_per_step = total_ms / args.steps
+    value = world * 1000.0 / ms_per_step
+    trace = [dict(node=r.node, N=r.N, steps=r.steps, err=r.err) for r in recs[:res.n_recs]]
+
+    # final error of the last cycle (outside the timed region, like the reference's report)
+    check = mg.run_cycle(path, base_flags & ~mg.RUN_NO_FINAL_ERROR)
+    mg_error = check["mg_error"]
+
+    # ---- end to end through the host-buffer ABI call ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hF = torch.empty(n, dtype=torch.float64).pin_memory()
+        hU = torch.empty(n, dtype=torch.float64).pin_memory()
+        lib.mgGridDownload(N, F.ptr, hF.data_ptr())
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def one_e2e():
+            rc = lib.mgRunCycleFileHost(os.fsencode(path), base_flags, hF.data_ptr(), hU.data_ptr(), recs, 64, res)
+            if rc != 0:
+                raise SystemExit("mgRunCycleFileHost failed: %d" % rc)
+
+        one_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            one_e2e()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1000.0 * wall)) / e2e_steps
+        e2e = {"value": world * 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+               "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "call": "mgRunCycleFileHost(cycle file, pinned F_host -> device, V-cycle, U -> pinned U_host)"}
+        del hF, hU
+
+    # ---- roofline of the dominant kernel, timed alone on the library's stream -----------------
+    hbm_peak, peak_src = peaks()
+    roof = dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, args.unfused)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Vcycle.txt shape (con_step=3, con_N=1, GS 1e-7 opt 1) at N_max=%d N_min=8, 1 grid per GPU" % N,
+                   "driver": "unfused (8 ABI operators)" if args.unfused else "fused (mgDownLeg/mgUpLeg)",
+                   "l2": "inputs exceed L2 (%.1f GiB per grid vs 126 MB)" % (8 * n / 2 ** 30),
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas (slab partition: see DESIGN.md)" % world},
+        "fine_dof_cycles_per_s": value * n,
+        "device_ms_per_cycle_node_loop": inner_ms / args.steps,
+        "mg_error": mg_error, "trace_errors": [t["err"] for t in trace if t["node"] != 0],
+        "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof,
+        "cycle_roofline": {"unfused_algorithmic_bytes": 357.0 * n, "achieved_GBs": 357.0 * n / (ms_per_step * 1e6),
+                           "note": "BASELINE.md 3: 357*N^2 B per unfused V-cycle; effective bandwidth may exceed HBM peak when legs are fused"},
+    }
+
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        kind, times, err = cpu_reference_run(args.ref_sample, threads, 2, N)
+        sec = min(times)
+        scale = (args.ref_sample / N) ** 2
+        line["cpu_baseline"] = {
+            "value": scale / sec, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "V-cycle N_max=%d, same shape, reference operators (-O0 -fopenmp as src/Makefile:8) on %d threads, "
+                      "best of 2, %.0f ms/cycle; scaled to N=%d by the DOF ratio" % (args.ref_sample, threads, 1000 * sec, N),
+            "sample_mg_error": err}
+    os.unlink(path)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, unfused):
+    """Times the kernel that dominates the V-cycle (the fine-grid smoothing pass) alone, with
+    CUDA events on the stream it is launched on; inputs (2 GiB grids) exceed L2."""
+    n = N * N
+    U, W, F = mg.DeviceGrid(N), mg.DeviceGrid(N), mg.DeviceGrid(N)
+    lib.getSource(N, 1.0, F.ptr, 0.0, 0.0)
+    lib.mgGridZero(N, U.ptr)
+    reps = 10
+    out = {}
+    # (a) one Jacobi sweep, out of place: reads U, F, writes U' = 24 B per point
+    for _ in range(3):
+        lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 1, W.ptr, None)
+    lib.mgSync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 1, W.ptr, None)
+    e1.record(stream)
+    lib.mgSync()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"bound": "hbm", "kernel": "k_sweep (one Jacobi sweep, fine grid N=%d)" % N, "achieved": 24.0 * n / (ms * 1e6),
+           "peak": hbm_peak, "unit": "GB/s", "frac": 24.0 * n / (ms * 1e6) / hbm_peak, "traffic": None,
+           "algorithmic_bytes_per_launch": 24.0 * n, "ms_per_launch": ms, "peak_source": peak_src}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,148 @@
+/*
+ * mg_abi.h -- C ABI of the B200-native multigrid Poisson hot path (libmgb200.so).
+ *
+ * This is the drop-in boundary for the reference's grid operators.  The reference
+ * has no FFI: its boundary is the set of free functions declared at
+ * /root/reference/src/MG_solver_CPU.cpp:16-34 (GPU twins MG_solver_GPU.cu:31-45),
+ * called only by main().  The eight operators below keep those names, argument
+ * order and meaning; the only change is that every grid pointer is a DEVICE
+ * pointer to a contiguous N x N fp64 array (index = ix + N*iy, boundary
+ * included).  Scalars returned through pointers (`error`) are HOST pointers and
+ * are valid when the call returns.
+ *
+ * All calls are issued by one host thread and are ordered on one CUDA stream per
+ * context.  There is no CPU fallback: every entry point aborts through the error
+ * channel (mgLastError) if the CUDA device is missing.
+ *
+ * Plain C, no C++/torch types in any signature.
+ */
+#ifndef MG_ABI_H
+#define MG_ABI_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ lifecycle
+ * The reference folds these into malloc/memset/free and cudaSetDevice(0)
+ * (MG_solver_GPU.cu:58; linkedlist.cpp:9-11,48-50). */
+int mgInit(int device);                 /* 0 on success; creates the context on `device` */
+void mgShutdown(void);
+int mgLastErrorCode(void);              /* 0 = no error since the last mgClearError */
+const char *mgLastError(void);
+void mgClearError(void);
+void mgSync(void);                      /* wait for everything queued so far */
+void *mgStream(void);                   /* the context's cudaStream_t (for event timing by callers) */
+int mgKernelLaunches(void);             /* kernels launched by this library since mgInit */
+
+double *mgGridAlloc(int N);             /* pooled device array of N*N doubles (uninitialised, like malloc) */
+void mgGridFree(double *grid);
+void mgGridZero(int N, double *grid);   /* memset(U, 0, ...)           MG_solver_CPU.cpp:213,256 */
+void mgGridNegate(int N, double *grid); /* D = -D                      MG_solver_CPU.cpp:277-280 */
+void mgGridUpload(int N, double *dev, const double *host);
+void mgGridDownload(int N, const double *dev, double *host);
+void mgGridCopy(int N, double *dst, const double *src);
+
+/* ------------------------------------------------------- the eight operators
+ * Same names / argument lists as the reference prototypes. */
+/* MG_solver_CPU.cpp:468-493 */
+void getSource(int N, double L, double *F, double min_x, double min_y);
+/* MG_solver_CPU.cpp:497-523 */
+void getBoundary(int N, double L, double *F, double min_x, double min_y);
+/* MG_solver_CPU.cpp:554-564 */
+void getResidual(int N, double L, double *U, double *F, double *D);
+/* MG_solver_CPU.cpp:573-625 -- `error` is a host pointer */
+void doSmoothing(int N, double L, double *U, double *F, int step, double *error);
+/* MG_solver_CPU.cpp:640-680 -- N fine, M coarse */
+void doRestriction(int N, double *U_f, int M, double *U_c);
+/* MG_solver_CPU.cpp:682-724 -- N coarse, M fine */
+void doProlongation(int N, double *U_c, int M, double *U_f);
+/* MG_solver_CPU.cpp:566-571 */
+void doGridAddition(int N, double *U1, double *U2);
+/* MG_solver_CPU.cpp:627-638 -- option 0 InverseMatrix (:758-950), 1 GaussSeidel (:952-1066) */
+void doExactSolver(int N, double L, double *U, double *F, double target_error, int option);
+
+/* MG_solver_CPU.cpp:525-548 */
+void getAnalytic(int N, double L, double *U, double min_x, double min_y);
+/* mean |analytic - U| of the final report, MG_solver_CPU.cpp:434-445 (synchronous) */
+double mgAnalyticError(int N, double L, const double *U, double min_x, double min_y);
+/* Gauss-Seidel iterations taken by the last doExactSolver(option 1) (synchronous) */
+int mgLastExactSolverIterations(void);
+
+/* ----------------------------------------------------------- fused operators
+ * What the cycle driver uses where the cycle permits.  Results are identical to
+ * the corresponding sequence of the eight operators.
+ *
+ * `error` arguments of the fused calls are HOST pointers obtained from
+ * mgScalarSlot(): pinned, device-visible doubles that the kernel itself writes.
+ * The value is valid after mgSync() (no per-call synchronisation). */
+double *mgScalarSlot(int index);        /* index in [0, MG_SCALAR_SLOTS) */
+#define MG_SCALAR_SLOTS 4096
+
+/* step Jacobi sweeps out of place (U_in untouched, result in U_out) + the
+ * reference's smoothing error.  == doSmoothing on a copy.  error_slot == NULL skips the
+ * error pass (then step == 1 is exactly one sweep kernel). */
+void mgSmooth(int N, double L, const double *U_in, double *F, int step, double *U_out, double *error_slot);
+
+/* the whole -1 node (MG_solver_CPU.cpp:246-287) without materialising D:
+ *   if zero_init: U = 0;  U <- step sweeps;  *error;  F_c <- doRestriction(N, -(getResidual(U,F)), M)
+ * U_work is scratch of N*N doubles (ping-pong partner); on return the smoothed
+ * grid is in the buffer the call returns (either U or U_work). */
+double *mgDownLeg(int N, double L, double *U, double *U_work, double *F, int step, int zero_init,
+                  int M, double *F_c, double *error_slot);
+
+/* doExactSolver that also reports its Gauss-Seidel iteration count (as a double, -1 for
+ * option 0) into a scalar slot, without synchronising. */
+void mgExactSolve(int N, double L, double *U, double *F, double target_error, int option, double *iters_slot);
+
+/* the whole 1 node (MG_solver_CPU.cpp:350-416) without materialising tempU:
+ *   U_f <- U_f + doProlongation(Nc, U_c, N);  U_f <- step sweeps;  *error
+ * returns the buffer holding the result (U_f or U_work). */
+double *mgUpLeg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, double *F, int step,
+                double *error_slot);
+
+/* ---------------------------------------------------------------- the driver
+ * Cycle.txt interpreter = the reference's main() loop (MG_solver_CPU.cpp:36-462)
+ * over a device-resident level stack (linkedlist.cpp). */
+typedef struct mgTraceRec {
+    int node;       /* -1, 0, 1 */
+    int N;          /* grid the node smoothed / solved on */
+    int steps;      /* sweeps done (trigger mode: counted); node 0: GS iterations or -1 */
+    double err;     /* smoothing error after the node (0 for node 0) */
+} mgTraceRec;
+
+typedef struct mgCycleResult {
+    int n_recs;
+    int N;              /* top-level grid size */
+    double mg_error;    /* mean |analytic - U| */
+    double time_ms;     /* device time of the node loop (CUDA events) */
+    double wall_ms;     /* host wall time of the node loop incl. final sync */
+    int launches;       /* kernels launched inside the node loop */
+} mgCycleResult;
+
+#define MG_RUN_FUSED 1          /* use mgDownLeg/mgUpLeg where the cycle permits (default path) */
+#define MG_RUN_UNFUSED 0        /* one of the eight operators per reference call */
+#define MG_RUN_QUIET 2          /* do not print the reference's stdout log */
+#define MG_RUN_SKIP_SOURCE 4    /* F of the top level is supplied by the caller (F_top, used in place, never written) */
+#define MG_RUN_NO_FINAL_ERROR 8 /* skip the analytic-error report after the node loop (mg_error = 0) */
+
+/* Runs a cycle file.  F_top (device, N_max^2) is used instead of getSource when
+ * MG_RUN_SKIP_SOURCE is set.  U_top, if non-NULL (device, N_max^2), receives the
+ * final solution.  Returns 0 on success. */
+int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_top,
+                   mgTraceRec *recs, int max_recs, mgCycleResult *res);
+
+/* Same with HOST buffers: F_host (N_max^2, may be NULL -> getSource on device) is
+ * copied to the device, the cycle runs, the solution is copied back into U_host. */
+int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double *U_host,
+                       mgTraceRec *recs, int max_recs, mgCycleResult *res);
+
+/* CSV dump in the reference's format (doPrint2File, MG_solver_CPU.cpp:735-754) from a host array */
+int mgPrint2File(int N, const double *U_host, const char *file_name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,13 @@
+"""B200-native geometric multigrid Poisson hot path.
+
+The product is the C-ABI shared library `libmgb200.so` (hand-written sm_100a CUDA kernels,
+C++ cycle driver; see include/mg_abi.h) plus the `MG_GPU` command line.  This package is the
+thin Python host mirror of that ABI used by the tests and bench.py: same operator names and
+argument meaning as the reference (MG_solver_CPU.cpp:16-34), grids resident on the device.
+
+There is no CPU fallback: importing works anywhere, but every operator needs the built
+library and a CUDA device and raises loudly otherwise.
+"""
+from .api import (MGLibraryError, DeviceGrid, GpuOps, init, lib, lib_path, run_cycle, run_cycle_host,  # noqa: F401
+                  RUN_FUSED, RUN_UNFUSED, RUN_QUIET, RUN_SKIP_SOURCE, RUN_NO_FINAL_ERROR)
+from . import cycles  # noqa: F401

@@ -1,0 +1,363 @@
+// mg_driver.cpp -- Cycle.txt interpreter over a device-resident level stack.
+//
+// Host-side C++ that calls only the C ABI of include/mg_abi.h.  It reproduces the control
+// flow of the reference's main() (MG_solver_CPU.cpp:36-462) and of its LinkedList level
+// stack (linkedlist.cpp:7-124): the same node stream, option parsing for all six
+// (con_step, con_N) cases, the U-zeroing rule, the init/restart flag, the error-trigger
+// loops, and the same stdout blocks.  Two execution modes:
+//   MG_RUN_UNFUSED  one ABI operator per reference call (literal drop-in)
+//   MG_RUN_FUSED    mgDownLeg / mgUpLeg per node, no D / tempU grids, no host sync per node
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/mg_abi.h"
+
+namespace {
+
+constexpr double TRIGGER = 0.01;  // MG_solver_CPU.cpp:99
+
+struct Level {
+    int N = 0;
+    double *U = nullptr;     // current solution buffer
+    double *W = nullptr;     // ping-pong partner of U (fused mode) / unused
+    double *F = nullptr;
+    double *D = nullptr;     // only materialised in unfused mode
+    int step = 0;
+    double smoothing_error = 0;
+    bool owns_F = true;      // false when F is the caller's top-level source used in place
+};
+
+struct Pending {  // a trace record whose scalar lives in a pinned slot until the next sync
+    int rec;
+    int slot;
+    bool is_iters;
+};
+
+class Cycle {
+public:
+    Cycle(int flags, mgTraceRec *recs, int max_recs) : flags_(flags), recs_(recs), max_recs_(max_recs) {}
+    ~Cycle() { while (!stack_.empty()) pop(); }
+
+    bool fused() const { return (flags_ & MG_RUN_FUSED) != 0; }
+    bool quiet() const { return (flags_ & MG_RUN_QUIET) != 0; }
+
+    void push(int N, double *borrowed_F = nullptr)  // linkedlist.cpp:7-44: three uninitialised arrays per node
+    {
+        Level l;
+        l.N = N;
+        l.U = mgGridAlloc(N);
+        l.F = borrowed_F ? borrowed_F : mgGridAlloc(N);
+        l.owns_F = borrowed_F == nullptr;
+        if (fused()) l.W = mgGridAlloc(N);
+        else l.D = mgGridAlloc(N);
+        stack_.push_back(l);
+    }
+    void pop()  // linkedlist.cpp:46-69
+    {
+        Level &l = stack_.back();
+        mgGridFree(l.U); mgGridFree(l.W); mgGridFree(l.D);
+        if (l.owns_F) mgGridFree(l.F);
+        stack_.pop_back();
+        if (stack_.size() == 1) init_ = 0;
+    }
+    Level &top() { return stack_.back(); }
+    size_t depth() const { return stack_.size(); }
+    bool restart_top() const { return init_ == 0 && stack_.size() == 1; }  // :209, :252
+
+    int next_slot()
+    {
+        if (slot_ == MG_SCALAR_SLOTS) harvest();
+        return slot_++;
+    }
+    // after a sync, move slot values into the trace records
+    void harvest()
+    {
+        mgSync();
+        for (const Pending &p : pending_) {
+            if (p.rec >= max_recs_ || !recs_) continue;
+            const double v = *mgScalarSlot(p.slot);
+            if (p.is_iters) recs_[p.rec].steps = (int)v;
+            else recs_[p.rec].err = v;
+        }
+        pending_.clear();
+        slot_ = 0;
+    }
+    int record(int node, int N, int steps, double err)
+    {
+        const int r = n_recs_++;
+        if (recs_ && r < max_recs_) { recs_[r].node = node; recs_[r].N = N; recs_[r].steps = steps; recs_[r].err = err; }
+        return r;
+    }
+    void defer(int rec, int slot, bool is_iters) { pending_.push_back({rec, slot, is_iters}); }
+    int n_recs() const { return n_recs_; }
+
+    // Error-trigger smoothing (:216-230 / :388-402): one sweep at a time, stop when two
+    // successive errors differ by <= TRIGGER; the host needs the scalar after every sweep.
+    int trigger_smooth(Level &l, double L)
+    {
+        double slope = TRIGGER + 1.0, previous = 0.0;
+        l.step = 0;
+        while (slope > TRIGGER) {
+            if (fused()) {
+                double *slot = mgScalarSlot(MG_SCALAR_SLOTS - 1);
+                mgSmooth(l.N, L, l.U, l.F, 1, l.W, slot);
+                std::swap(l.U, l.W);
+                mgSync();
+                l.smoothing_error = *slot;
+            } else {
+                doSmoothing(l.N, L, l.U, l.F, 1, &l.smoothing_error);
+            }
+            l.step += 1;
+            if (l.step > 1) slope = std::fabs(l.smoothing_error - previous);
+            previous = l.smoothing_error;
+            if (mgLastErrorCode()) break;
+        }
+        return l.step;
+    }
+
+    void log_smoothing(const Level &l, int steps)
+    {
+        if (quiet()) return;
+        printf("          ~Smoothing~\n");
+        printf("Current Grid Size N = %d\n", l.N);
+        printf("    Smoothing Steps = %d\n", steps);
+        printf("              Error = %lf\n", l.smoothing_error);
+    }
+
+    int flags_;
+    mgTraceRec *recs_;
+    int max_recs_;
+    int n_recs_ = 0;
+    int init_ = 1;  // linkedlist.h:41-44
+    int slot_ = 0;
+    std::vector<Level> stack_;
+    std::vector<Pending> pending_;
+};
+
+const char *kRestrictArt = "             *\n             |\n Restriction |\n             |\n             *\n";
+const char *kProlongArt = "             *\n             |\nProlongation |\n             |\n             *\n";
+
+int run(const char *path, int flags, const double *F_top, double *U_top, mgTraceRec *recs, int max_recs,
+        mgCycleResult *res)
+{
+    std::ifstream f(path);
+    if (!f.is_open()) {
+        fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path);
+        return 1;
+    }
+    double L, min_x, min_y;
+    int con_step, con_N, N_max, N_min;
+    f >> L >> min_x >> min_y;   // :103
+    f >> con_step >> con_N;     // :106
+    f >> N_max >> N_min;        // :109
+    if (!f) return 2;
+
+    std::vector<int> ladder;    // :111-146
+    if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
+    if (con_N == 2) for (int n = N_max; n >= N_min; --n) ladder.push_back(n);
+    size_t pos = 0;
+
+    Cycle cy(flags, recs, max_recs);
+    const bool fused = cy.fused(), quiet = cy.quiet();
+    // In fused mode the log needs each node's error, which costs a sync per node; quiet runs stay asynchronous.
+    const bool sync_each_node = fused && !quiet;
+
+    if ((flags & MG_RUN_SKIP_SOURCE) && F_top) {
+        cy.push(N_max, const_cast<double *>(F_top));                  // the operators never write F
+    } else {
+        cy.push(N_max);                                               // :149
+        getSource(N_max, L, cy.top().F, min_x, min_y);                // :153 (outside the timer)
+    }
+    mgSync();
+
+    cudaStream_t stream = (cudaStream_t)mgStream();
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    const int launches0 = mgKernelLaunches();
+    const auto wall0 = std::chrono::steady_clock::now();
+    cudaEventRecord(ev0, stream);                                     // :156
+
+    int rc = 0;
+    int node = 0;
+    while (f >> node) {                                               // :158-160 (stops at EOF instead of re-running)
+        if (node == 2) break;                                         // :162
+        if (mgLastErrorCode()) { rc = 10; break; }
+
+        if (node == -1) {                                             // :169-301
+            int step, next_N;
+            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
+            if (con_N == 0) { if (!(f >> next_N)) { rc = 3; break; } }
+            else {
+                if (pos + 1 >= ladder.size()) { rc = 4; break; }
+                next_N = ladder[++pos];
+            }
+            if (step == 0) continue;                                  // :241-243, :296-299 (FMG placeholder)
+            Level *l = &cy.top();
+            const bool zero_init = !cy.restart_top();                 // :209-214 / :252-257
+            const int fine_N = l->N;
+
+            if (fused && step > 0) {
+                const int slot = cy.next_slot();
+                cy.push(next_N);
+                l = &cy.stack_[cy.depth() - 2];
+                Level &c = cy.top();
+                double *resbuf = mgDownLeg(fine_N, L, l->U, l->W, l->F, step, zero_init, next_N, c.F, mgScalarSlot(slot));
+                if (resbuf != l->U) std::swap(l->U, l->W);
+                l->step = step;
+                const int r = cy.record(-1, fine_N, step, 0.0);
+                cy.defer(r, slot, false);
+                if (sync_each_node) { cy.harvest(); l->smoothing_error = *mgScalarSlot(slot); }
+                if (!quiet) { cy.log_smoothing(*l, step); fputs(kRestrictArt, stdout); }
+                continue;
+            }
+
+            if (zero_init) mgGridZero(l->N, l->U);
+            int done;
+            if (step == -1) done = cy.trigger_smooth(*l, L);
+            else { doSmoothing(l->N, L, l->U, l->F, step, &l->smoothing_error); l->step = done = step; }
+            if (!quiet) cy.log_smoothing(*l, done);
+            cy.record(-1, l->N, done, l->smoothing_error);
+
+            if (fused) {
+                // trigger mode in the fused driver: residual + negate + restrict without sweeps
+                cy.push(next_N);
+                l = &cy.stack_[cy.depth() - 2];
+                mgDownLeg(fine_N, L, l->U, l->W, l->F, 0, 0, next_N, cy.top().F, nullptr);
+            } else {
+                getResidual(l->N, L, l->U, l->F, l->D);               // :239 / :268
+                mgGridNegate(l->N, l->D);                             // :277-280
+                cy.push(next_N);                                      // :283
+                l = &cy.stack_[cy.depth() - 2];
+                doRestriction(fine_N, l->D, next_N, cy.top().F);      // :287
+            }
+            if (!quiet) fputs(kRestrictArt, stdout);
+        } else if (node == 0) {                                       // :305-325
+            double target; int option;
+            if (!(f >> target >> option)) { rc = 3; break; }
+            Level &l = cy.top();
+            const int slot = cy.next_slot();
+            mgExactSolve(l.N, L, l.U, l.F, target, option, mgScalarSlot(slot));
+            const int r = cy.record(0, l.N, -1, 0.0);
+            cy.defer(r, slot, true);
+            if (!quiet) {
+                printf("          ~Exact Solver~\n");
+                printf("Current Grid Size N = %d\n", l.N);
+                if (option == 0) printf("   Use Exact Solver = Inverse Matrix\n");
+                if (option == 1) printf("   Use Exact Solver = GaussSeidel Even / Odd\n");
+                printf("       Target Error = %.3e\n", target);
+            }
+        } else if (node == 1) {                                       // :329-424
+            int step;
+            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
+            if (con_N != 0 && pos > 0) --pos;
+            if (cy.depth() < 2) { rc = 5; break; }                    // reference: null prevNode
+            Level coarse = cy.top();
+            Level *l = &cy.stack_[cy.depth() - 2];
+
+            if (fused) {
+                const int slot = step > 0 ? cy.next_slot() : -1;
+                double *resbuf = mgUpLeg(coarse.N, coarse.U, l->N, L, l->U, l->W, l->F, step > 0 ? step : 0,
+                                         slot >= 0 ? mgScalarSlot(slot) : nullptr);
+                if (resbuf != l->U) std::swap(l->U, l->W);
+                if (!quiet) fputs(kProlongArt, stdout);
+                cy.pop();                                             // stream-ordered: safe to recycle the coarse grids
+                l = &cy.top();
+                int done = 0;
+                if (step == -1) done = cy.trigger_smooth(*l, L);
+                else if (step > 0) { l->step = done = step; }
+                const int r = cy.record(1, l->N, done, step == -1 ? l->smoothing_error : 0.0);
+                if (slot >= 0) {
+                    cy.defer(r, slot, false);
+                    if (sync_each_node) { cy.harvest(); l->smoothing_error = *mgScalarSlot(slot); }
+                }
+                if (!quiet && step != 0) cy.log_smoothing(*l, done);
+                continue;
+            }
+
+            double *tmp = mgGridAlloc(l->N);                          // :353
+            doProlongation(coarse.N, coarse.U, l->N, tmp);            // :354
+            if (!quiet) fputs(kProlongArt, stdout);
+            cy.pop();                                                 // :363
+            l = &cy.top();
+            doGridAddition(l->N, l->U, tmp);                          // :368
+            mgGridFree(tmp);                                          // :371
+            int done = 0;
+            if (step == -1) done = cy.trigger_smooth(*l, L);
+            else if (step > 0) { doSmoothing(l->N, L, l->U, l->F, step, &l->smoothing_error); l->step = done = step; }
+            if (!quiet && step != 0) cy.log_smoothing(*l, done);
+            cy.record(1, l->N, done, l->smoothing_error);
+        } else {
+            rc = 6;
+            break;
+        }
+    }
+    cudaEventRecord(ev1, stream);                                     // :429
+    cy.harvest();
+    const auto wall1 = std::chrono::steady_clock::now();
+    if (mgLastErrorCode() && rc == 0) rc = 10;
+
+    if (res) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        res->time_ms = ms;
+        res->wall_ms = std::chrono::duration<double, std::milli>(wall1 - wall0).count();
+        res->launches = mgKernelLaunches() - launches0;
+        res->n_recs = cy.n_recs() < max_recs ? cy.n_recs() : max_recs;
+        res->N = cy.stack_.empty() ? 0 : cy.stack_.front().N;
+        res->mg_error = 0.0;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+
+    if (rc == 0 && !cy.stack_.empty()) {
+        Level &l = cy.top();
+        if (res && !(flags & MG_RUN_NO_FINAL_ERROR)) res->mg_error = mgAnalyticError(l.N, L, l.U, min_x, min_y);   // :434-445
+        if (U_top) { mgGridCopy(l.N, U_top, l.U); mgSync(); }
+        if (!quiet && res) {
+            printf("\n\n");
+            printf("===== Final Result =====\n");
+            printf("    Error = %lf\n", res->mg_error);
+            printf("Time Used = %lf (ms)\n", res->wall_ms);
+        }
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_top, mgTraceRec *recs,
+                              int max_recs, mgCycleResult *res)
+{
+    if (mgLastErrorCode()) return 10;
+    return run(path, flags, F_top, U_top, recs, max_recs, res);
+}
+
+extern "C" int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double *U_host, mgTraceRec *recs,
+                                  int max_recs, mgCycleResult *res)
+{
+    if (mgLastErrorCode()) return 10;
+    // peek N_max for the staging grids
+    std::ifstream f(path);
+    if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
+    double L, mx, my; int cs, cn, N_max, N_min;
+    f >> L >> mx >> my >> cs >> cn >> N_max >> N_min;
+    if (!f) return 2;
+    f.close();
+    double *dF = nullptr, *dU = nullptr;
+    if (F_host) { dF = mgGridAlloc(N_max); mgGridUpload(N_max, dF, F_host); flags |= MG_RUN_SKIP_SOURCE; }
+    if (U_host) dU = mgGridAlloc(N_max);
+    const int rc = run(path, flags, dF, dU, recs, max_recs, res);
+    if (rc == 0 && U_host) mgGridDownload(N_max, dU, U_host);
+    mgGridFree(dF);
+    mgGridFree(dU);
+    return rc;
+}
