@@ -1,16 +1,224 @@
-// mg_fused.cu -- smoothing passes and the fused -1 / 1 cycle legs.
+// mg_fused.cu -- smoothing passes and the fused -1 / 1 cycle legs, built on the
+// register-streaming kernel of mg_stream.cuh.  Odd grid sizes (rows not 16-byte aligned) and
+// transfer pairs whose restriction map is not injective take the baseline kernels of
+// mg_kernels.cu instead; both paths produce identical bits.
 #include "mg_fused.h"
 
-#include "mg_device.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
 #include "mg_kernels.h"
+#include "mg_stream.cuh"
 
 namespace mg {
+namespace {
 
-void fused_init() {}
+struct FusedRestrictTable {
+    bool usable = false;
+    int *f2c = nullptr;     // device [N]
+    double *rw = nullptr;   // device [M]
+};
+std::map<std::pair<int, int>, FusedRestrictTable> g_restrict_tables;
+int g_force_H = 0;
+bool g_disable = false;
+
+// Host construction of the restriction map with the very libm calls the reference makes
+// (MG_solver_CPU.cpp:661-664), inverted: f2c[f] = coarse index t with floor(t*h_c/h_f) == f.
+// Coarse boundary indices are mapped too (their value is forced to 0 by the kernel): 0 -> 0
+// and M-1 -> N-2.  Unusable (-> baseline kernels) if two coarse indices share a fine index.
+const FusedRestrictTable &fused_restrict_table(int N, int M)
+{
+    auto it = g_restrict_tables.find({N, M});
+    if (it != g_restrict_tables.end()) return it->second;
+    FusedRestrictTable t;
+    if (M >= 3 && M < N && N >= 4) {
+        const double h_f = 1.0 / (double)(N - 1), h_c = 1.0 / (double)(M - 1);
+        std::vector<int> f2c((size_t)N, -1);
+        std::vector<double> rw((size_t)M, 0.0);
+        bool ok = true;
+        for (int c = 1; c <= M - 2 && ok; ++c) {
+            const double pos = (double)c * h_c;
+            const int f = (int)floor(pos / h_f);
+            rw[c] = fmod(pos, h_f) / h_f;
+            if (f < 1 || f > N - 3 || f2c[f] != -1) ok = false;   // f+1 must stay inside, map must be injective
+            else f2c[f] = c;
+        }
+        if (ok && f2c[0] == -1 && f2c[N - 2] == -1) {
+            f2c[0] = 0;
+            f2c[N - 2] = M - 1;
+            bool good = check(cudaMalloc(&t.f2c, (size_t)N * sizeof(int)), "cudaMalloc f2c");
+            good = good && check(cudaMalloc(&t.rw, (size_t)M * sizeof(double)), "cudaMalloc rw");
+            // synchronous copies from pageable memory: the vectors die at the end of this scope
+            good = good && check(cudaMemcpy(t.f2c, f2c.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice), "H2D f2c");
+            good = good && check(cudaMemcpy(t.rw, rw.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice), "H2D rw");
+            t.usable = good;
+        }
+    }
+    return g_restrict_tables.emplace(std::make_pair(N, M), t).first->second;
+}
+
+template <int S, int IN, bool ERR, bool RES>
+void launch_stream(StreamParams &p)
+{
+    using G = StreamGeo<S, ERR || RES, RES>;
+    Context &c = ctx();
+    const int N = p.N;
+    p.n_strips = (N + G::W - 1) / G::W;
+    p.n_sgroups = (p.n_strips + STREAM_WARPS - 1) / STREAM_WARPS;
+    // rows per task: enough CTAs to fill the chip twice, at most 256 rows (halo rows cost (2S+3)/H)
+    int H = g_force_H;
+    if (H <= 0) {
+        const int target_blocks = 2 * c.sm_count;
+        int n_segs = std::max(1, target_blocks / p.n_sgroups);
+        n_segs = std::min(n_segs, (N + 15) / 16);
+        H = (N + n_segs - 1) / n_segs;
+        H = std::min(256, (H + 7) / 8 * 8);
+    }
+    p.H = H;
+    p.n_segs = (N + H - 1) / H;
+    const unsigned blocks = (unsigned)p.n_sgroups * (unsigned)p.n_segs;
+    if (ERR) {
+        p.partials = partials_buf(blocks);
+        p.counter = c.counters;
+    }
+    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, 0, c.stream>>>(p);
+    c.launches++;
+    check(cudaGetLastError(), "k_stream");
+}
+
+template <int IN, bool ERR, bool RES>
+void launch_stream_s(int S, StreamParams &p)
+{
+    switch (S) {
+        case 0: launch_stream<0, IN, ERR, RES>(p); break;
+        case 1: launch_stream<1, IN, ERR, RES>(p); break;
+        case 2: launch_stream<2, IN, ERR, RES>(p); break;
+        default: launch_stream<3, IN, ERR, RES>(p); break;
+    }
+}
+
+// mode: 0 plain, 1 ERR, 2 ERR+RES
+void launch_stream_any(int S, int in, int mode, StreamParams &p)
+{
+    if (in == IN_LOAD) {
+        if (mode == 0) launch_stream_s<IN_LOAD, false, false>(S, p);
+        else if (mode == 1) launch_stream_s<IN_LOAD, true, false>(S, p);
+        else launch_stream_s<IN_LOAD, true, true>(S, p);
+    } else if (in == IN_ZERO) {
+        if (mode == 0) launch_stream_s<IN_ZERO, false, false>(S, p);
+        else if (mode == 1) launch_stream_s<IN_ZERO, true, false>(S, p);
+        else launch_stream_s<IN_ZERO, true, true>(S, p);
+    } else {
+        if (mode == 0) launch_stream_s<IN_PROLONG, false, false>(S, p);
+        else launch_stream_s<IN_PROLONG, true, false>(S, p);
+    }
+}
+
+bool streamable(int N) { return !g_disable && N >= 4 && (N % 2 == 0); }
+
+// Split `step` sweeps into passes of at most STREAM_SMAX, as evenly as possible.
+std::vector<int> split_passes(int step)
+{
+    std::vector<int> out;
+    if (step <= 0) return out;
+    const int n = (step + STREAM_SMAX - 1) / STREAM_SMAX;
+    for (int k = 0; k < n; ++k) out.push_back(step / n + (k < step % n ? 1 : 0));
+    return out;
+}
+
+struct LegSpec {
+    int in = IN_LOAD;          // level 0 of the FIRST pass
+    bool want_err = false;     // error after the LAST pass
+    bool want_res = false;     // restriction after the LAST pass
+    // prolongation (first pass)
+    int Nc = 0;
+    const double *Uc = nullptr;
+    // restriction (last pass)
+    int M = 0;
+    double *Fc = nullptr;
+    double *err_dev = nullptr, *err_slot = nullptr;
+};
+
+// Runs the passes of one leg on even N.  `a` holds the input of the first pass (unless IN_ZERO),
+// `b` is the ping-pong partner.  Returns the buffer holding the final level.
+double *run_leg(int N, double L, double *a, double *b, const double *F, int step, const LegSpec &spec)
+{
+    const Spacing sp = spacing(N, L);
+    std::vector<int> passes = split_passes(step);
+    if (passes.empty()) passes.push_back(0);   // a pass without sweeps (prolong-add only / residual+restrict only)
+    double *src = a, *dst = b;
+    for (size_t k = 0; k < passes.size(); ++k) {
+        const bool first = k == 0, last = k + 1 == passes.size();
+        StreamParams p{};
+        p.N = N;
+        p.h2 = sp.h2;
+        p.inv_h2 = sp.inv_h2;
+        p.F = F;
+        const int in = first ? spec.in : IN_LOAD;
+        p.Uin = src;
+        // An IN_ZERO pass reads nothing, so it may write straight into `a`.
+        double *out = (in == IN_ZERO) ? src : dst;
+        p.Uout = out;
+        int mode = 0;
+        if (last && spec.want_res) mode = 2;
+        else if (last && spec.want_err) mode = 1;
+        if (mode >= 1) {
+            p.err_dev = spec.err_dev;
+            p.err_slot = spec.err_slot;
+        }
+        if (mode == 2) {
+            const FusedRestrictTable &t = fused_restrict_table(N, spec.M);
+            p.M = spec.M;
+            p.Fc = spec.Fc;
+            p.f2c = t.f2c;
+            p.rw = t.rw;
+        }
+        if (in == IN_PROLONG) {
+            const ProlongTable &t = prolong_table(spec.Nc, N);
+            p.Nc = spec.Nc;
+            p.Uc = spec.Uc;
+            p.row_cell = t.row_cell;
+            p.col_cell = t.col_cell;
+            p.row_w = t.row_w;
+            p.col_w = t.col_w;
+            p.c_dx = 1.0 / (double)(spec.Nc - 1);
+            p.inv_c_dx = 1.0 / p.c_dx;
+        }
+        if (passes[k] == 0 && in == IN_LOAD && mode == 0) break;   // nothing to do
+        if (passes[k] == 0 && in == IN_LOAD) {
+            // residual / restriction of the input itself: no new level is produced, keep `src`
+            p.Uout = nullptr;   // level S is the input itself: nothing to write
+            launch_stream_any(0, in, mode, p);
+            continue;
+        }
+        launch_stream_any(passes[k], in, mode, p);
+        if (out == dst) std::swap(src, dst);
+    }
+    return src;
+}
+
+}  // namespace
+
+void fused_init()
+{
+    if (const char *h = getenv("MG_STREAM_H")) g_force_H = atoi(h);
+    if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
+}
 
 double *smooth_out_of_place(int N, double L, double *a, double *b, const double *F, int step, bool in_is_zero,
                             double *err_dev, double *err_slot)
 {
+    const bool want_err = err_dev || err_slot;
+    if (streamable(N) && (step > 0 || want_err)) {
+        if (step == 0 && in_is_zero) check(cudaMemsetAsync(a, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
+        LegSpec spec;
+        spec.in = (in_is_zero && step > 0) ? IN_ZERO : IN_LOAD;
+        spec.want_err = want_err;
+        spec.err_dev = err_dev;
+        spec.err_slot = err_slot;
+        return run_leg(N, L, a, b, F, step, spec);
+    }
     const Spacing sp = spacing(N, L);
     double *cur = a, *other = b;
     for (int s = 0; s < step; ++s) {
@@ -18,18 +226,29 @@ double *smooth_out_of_place(int N, double L, double *a, double *b, const double 
             launch_sweep(N, sp.h2, cur, F, cur, true);  // the input is implied zeros: safe in place
         } else {
             launch_sweep(N, sp.h2, cur, F, other, false);
-            double *t = cur; cur = other; other = t;
+            std::swap(cur, other);
         }
     }
-    if (step == 0 && in_is_zero)
-        check(cudaMemsetAsync(cur, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
-    if (err_dev || err_slot) launch_smooth_error(N, sp.inv_h2, cur, F, err_dev, err_slot);
+    if (step == 0 && in_is_zero) check(cudaMemsetAsync(cur, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
+    if (want_err) launch_smooth_error(N, sp.inv_h2, cur, F, err_dev, err_slot);
     return cur;
 }
 
 double *down_leg(int N, double L, double *U, double *U_work, const double *F, int step, bool zero_init, int M,
                  double *F_c, double *err_slot)
 {
+    if (streamable(N) && fused_restrict_table(N, M).usable) {
+        if (step == 0 && zero_init) check(cudaMemsetAsync(U, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
+        LegSpec spec;
+        spec.in = (zero_init && step > 0) ? IN_ZERO : IN_LOAD;
+        spec.want_err = true;
+        spec.want_res = true;
+        spec.M = M;
+        spec.Fc = F_c;
+        spec.err_dev = step > 0 ? ctx().dev_scalar : nullptr;
+        spec.err_slot = step > 0 ? err_slot : nullptr;
+        return run_leg(N, L, U, U_work, F, step, spec);
+    }
     const Spacing sp = spacing(N, L);
     double *res = smooth_out_of_place(N, L, U, U_work, F, step, zero_init, step > 0 ? ctx().dev_scalar : nullptr,
                                       step > 0 ? err_slot : nullptr);
@@ -44,6 +263,16 @@ double *down_leg(int N, double L, double *U, double *U_work, const double *F, in
 double *up_leg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, const double *F, int step,
                double *err_slot)
 {
+    if (streamable(N) && Nc >= 2) {
+        LegSpec spec;
+        spec.in = IN_PROLONG;
+        spec.Nc = Nc;
+        spec.Uc = U_c;
+        spec.want_err = step > 0;
+        spec.err_dev = step > 0 ? ctx().dev_scalar : nullptr;
+        spec.err_slot = step > 0 ? err_slot : nullptr;
+        return run_leg(N, L, U_f, U_work, F, step > 0 ? step : 0, spec);
+    }
     launch_prolong(Nc, U_c, N, U_f, U_f);
     if (step <= 0) return U_f;
     return smooth_out_of_place(N, L, U_f, U_work, F, step, false, ctx().dev_scalar, err_slot);

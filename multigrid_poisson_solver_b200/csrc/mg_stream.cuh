@@ -1,0 +1,297 @@
+// mg_stream.cuh -- the temporally blocked, register-streaming stencil kernel.
+//
+// One kernel template covers every fused pass of the cycle:
+//
+//   level 0 (input)   IN_LOAD     U_in                                   (smoothing pass)
+//                     IN_ZERO     0                                      (-1 node: U = 0, :252-257)
+//                     IN_PROLONG  U_f + doProlongation(U_c)              (1 node: :354 + :368)
+//   levels 1..S       S Jacobi sweeps (doSmoothing, :578-601), all in registers
+//   residual stage    ERR: the red-parity error sum of doSmoothing (:607-622)
+//                     RES: F_c = doRestriction(-(getResidual(U_S, F)))   (:268, :277-280, :287)
+//
+// Work decomposition.  A WARP owns a strip of W columns x H rows.  It streams down the rows of
+// a 64-column window (2 adjacent columns per lane, one 16-byte load per lane and row, 512
+// contiguous bytes per warp and row) that overlaps the neighbouring strips by the halo the S
+// sweeps (+ residual, + restriction) consume; at step r it loads row r of level 0 and produces
+// row r-1 of level 1, row r-2 of level 2, ... row r-S of level S and residual row r-S-1, so
+// every level keeps only two rows per lane in registers and nothing but the final level is ever
+// written.  Left/right neighbours come from the adjacent lanes by warp shuffle; there is no
+// shared memory and no CTA barrier in the streaming loop.  Warps are independent, so the halo is
+// recomputed rather than exchanged: 64/W in x and (H+2S+3)/H in y.
+//
+// Compulsory HBM traffic per fine point (fp64): smoothing pass 24 B (U in, F in, U out) for S
+// sweeps instead of 24*S; -1 node 16 B + 8 B per coarse point (F in, U out, F_c out) instead of
+// 146 B unfused; 1 node 24 B + 8 B per coarse point instead of 122 B.
+//
+// Bit parity: every expression uses the reference's association through mg_device.cuh.  The only
+// fused-multiply-adds are (a) s4 - 4*u, exact because 4*u is exact, and (b) the quotient
+// refinement of x / c_dx in the prolongation, which is correctly rounded (Markstein) and falls
+// back to an IEEE division outside a safe exponent range.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mg_device.cuh"
+
+namespace mg {
+
+enum { IN_LOAD = 0, IN_ZERO = 1, IN_PROLONG = 2 };
+
+constexpr int STREAM_WARPS = 8;         // warps (= strips) per CTA
+constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
+
+struct StreamParams {
+    int N;                  // grid size (even)
+    int H;                  // rows owned by one task
+    int n_strips, n_sgroups, n_segs;
+    double h2, inv_h2;
+    const double *Uin;      // IN_LOAD: U ; IN_PROLONG: U_f
+    const double *F;
+    double *Uout;
+    // ERR
+    double *partials;
+    unsigned int *counter;
+    double *err_dev, *err_slot;
+    // RES (restriction of the negated residual)
+    int M;
+    double *Fc;
+    const int *f2c;         // [N]  fine index -> coarse index whose lower-left fine point it is, or -1
+    const double *rw;       // [M]  fmod weight of the coarse index
+    // IN_PROLONG
+    int Nc;
+    const double *Uc;
+    const int *row_cell, *col_cell;
+    const double2 *row_w, *col_w;
+    double c_dx, inv_c_dx;
+};
+
+template <int S, bool NEED_R, bool RES>
+struct StreamGeo {
+    static constexpr int HL = (S + (NEED_R ? 1 : 0) + 1) / 2 * 2;                 // left halo, even (16-byte loads)
+    static constexpr int HR = S + (RES ? 2 : NEED_R ? 1 : 0);                    // right halo
+    static constexpr int W = (64 - HL - HR) / 2 * 2;                             // owned columns per strip, even
+    static constexpr int ROW_LEAD = S + (NEED_R ? 1 : 0);                        // rows streamed before the first owned row
+    static constexpr int ROW_TAIL = S + (RES ? 2 : NEED_R ? 1 : 0);              // steps after the last owned row
+};
+
+// x / d, correctly rounded, with y = 1/d (correctly rounded, host side).  Two Newton
+// corrections make the quotient faithful, then Markstein's final step rounds it correctly.
+__device__ __forceinline__ double div_by_invariant(double x, double d, double y)
+{
+    const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+    if (e - 200u > 1600u) return __ddiv_rn(x, d);   // zero, subnormal, huge, inf, nan: IEEE path
+    const double q0 = __dmul_rn(x, y);
+    const double r0 = __fma_rn(-q0, d, x);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-q1, d, x);
+    return __fma_rn(r1, y, q1);
+}
+
+// s4 - 4*u with one rounding == the reference's (s4 - RN(4*u)) because 4*u is exact.
+__device__ __forceinline__ double sub4(double s4, double u) { return __fma_rn(-4.0, u, s4); }
+
+__device__ __forceinline__ double jacobi_fast(double u, double s4, double h2f)
+{
+    return __dadd_rn(u, __dmul_rn(0.25, __dsub_rn(sub4(s4, u), h2f)));
+}
+__device__ __forceinline__ double residual_fast(double u, double s4, double f, double inv_h2)
+{
+    return __dsub_rn(__dmul_rn(inv_h2, sub4(s4, u)), f);
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <int S, int IN, bool ERR, bool RES>
+__global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamParams p)
+{
+    constexpr bool NEED_R = ERR || RES;
+    using G = StreamGeo<S, NEED_R, RES>;
+    constexpr int NF = S + (NEED_R ? 1 : 0);     // F rows kept: fw[k] = F row (r-1-k)
+    constexpr int NL = S + (NEED_R ? 1 : 0);     // levels that keep a two-row window
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.N;
+    const int seg = blockIdx.x / p.n_sgroups;
+    const int strip = (blockIdx.x % p.n_sgroups) * STREAM_WARPS + warp;
+    const bool active = strip < p.n_strips;
+
+    const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
+    const int cx = own_c_lo - G::HL + 2 * lane;                 // this lane's columns: cx, cx+1 (cx even)
+    const bool col_ok = active && cx >= 0 && cx < N;            // N even => cx+1 < N too
+    const bool col_own = col_ok && cx >= own_c_lo && cx < own_c_hi;
+    const bool x_in = cx > 0, y_in = cx + 1 < N - 1;            // interior columns
+    const int own_r_lo = seg * p.H, own_r_hi = min(own_r_lo + p.H, N);
+    const int r_first = max(0, own_r_lo - G::ROW_LEAD);
+    const int r_last = active ? min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD) : -1;   // idle warps skip the loop
+
+    const double h2 = p.h2, inv_h2 = p.inv_h2;
+    const double *__restrict__ Fp = p.F;
+    const double *__restrict__ Up = p.Uin;
+
+    double2 lo[NL > 0 ? NL : 1], mid[NL > 0 ? NL : 1], fw[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int t = 0; t < (NL > 0 ? NL : 1); ++t) lo[t] = mid[t] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int t = 0; t < (NF > 0 ? NF : 1); ++t) fw[t] = make_double2(0.0, 0.0);
+
+    // ---- restriction state
+    double2 d_prev = make_double2(0.0, 0.0);
+    int ccx = -1, ccy = -1;
+    double ax = 0.0, ay = 0.0;
+    if (RES && col_own) {
+        ccx = p.f2c[cx];
+        ccy = p.f2c[cx + 1];
+        if (ccx >= 0) ax = p.rw[ccx];
+        if (ccy >= 0) ay = p.rw[ccy];
+    }
+    // ---- prolongation state
+    int cqx = 0, cqy = 0, prev_rq = -4;
+    double2 wcx = make_double2(0.0, 0.0), wcy = wcx, bot = wcx, top = wcx;
+    if (IN == IN_PROLONG && col_ok) {
+        cqx = p.col_cell[cx];
+        cqy = p.col_cell[cx + 1];
+        wcx = p.col_w[cx];
+        wcy = p.col_w[cx + 1];
+    }
+    double err_acc = 0.0;
+
+    // ---- two-deep register prefetch of the streamed rows
+    double2 pu[2], pf[2];
+    auto fetch = [&](int r, double2 &u, double2 &f) {
+        u = make_double2(0.0, 0.0);
+        f = make_double2(0.0, 0.0);
+        if (!col_ok) return;
+        if (IN != IN_ZERO && r <= N - 1) u = ld2(Up + (size_t)r * N + cx);
+        if (NF > 0 && r >= 1 && r <= N) f = ld2(Fp + (size_t)(r - 1) * N + cx);   // F row r-1 is first used at step r
+    };
+    fetch(r_first, pu[0], pf[0]);
+    fetch(r_first + 1, pu[1], pf[1]);
+
+    for (int rb = r_first; rb <= r_last; rb += 2) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = rb + k;
+            if (r > r_last) break;
+            double2 x = pu[k];
+            const double2 f_new = pf[k];
+            fetch(r + 2, pu[k], pf[k]);
+
+            // ---- level 0 of the 1 node: U_f + P(U_c)
+            if (IN == IN_PROLONG && r <= N - 1) {
+                const int rq = p.row_cell[r];
+                const double2 wr = p.row_w[r];
+                if (rq != prev_rq) {
+                    const double *c_lo = p.Uc + (size_t)rq * p.Nc, *c_hi = c_lo + p.Nc;
+                    if (col_ok) {
+                        if (rq == prev_rq + 1) bot = top;
+                        else {
+                            bot.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
+                            bot.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
+                        }
+                        top.x = __dadd_rn(__dmul_rn(c_hi[cqx], wcx.x), __dmul_rn(c_hi[cqx + 1], wcx.y));
+                        top.y = __dadd_rn(__dmul_rn(c_hi[cqy], wcy.x), __dmul_rn(c_hi[cqy + 1], wcy.y));
+                    }
+                    prev_rq = rq;
+                }
+                const double vx = __dadd_rn(__dmul_rn(bot.x, wr.x), __dmul_rn(top.x, wr.y));
+                const double vy = __dadd_rn(__dmul_rn(bot.y, wr.x), __dmul_rn(top.y, wr.y));
+                x.x = __dadd_rn(x.x, div_by_invariant(div_by_invariant(vx, p.c_dx, p.inv_c_dx), p.c_dx, p.inv_c_dx));
+                x.y = __dadd_rn(x.y, div_by_invariant(div_by_invariant(vy, p.c_dx, p.inv_c_dx), p.c_dx, p.inv_c_dx));
+            }
+
+            // ---- shift the F window
+#pragma unroll
+            for (int t = NF - 1; t > 0; --t) fw[t] = fw[t - 1];
+            if (NF > 0) fw[0] = f_new;
+
+            // ---- S sweeps: level t row (r-t-1) -> level t+1
+#pragma unroll
+            for (int t = 0; t < S; ++t) {
+                const int i = r - t - 1;
+                const double2 c = mid[t];
+                double2 nx = c;                                   // boundary rows/columns are carried over
+                if (i > 0 && i < N - 1) {
+                    const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
+                    if (x_in) nx.x = jacobi_fast(c.x, sum4(x.x, lo[t].x, c.y, left), __dmul_rn(h2, fw[t].x));
+                    if (y_in) nx.y = jacobi_fast(c.y, sum4(x.y, lo[t].y, right, c.x), __dmul_rn(h2, fw[t].y));
+                }
+                lo[t] = c;
+                mid[t] = x;
+                x = nx;
+            }
+
+            // ---- x is now level S, row r-S
+            {
+                const int i = r - S;
+                if (p.Uout && i >= own_r_lo && i < own_r_hi && col_own) *reinterpret_cast<double2 *>(p.Uout + (size_t)i * N + cx) = x;
+            }
+
+            if (NEED_R) {
+                const int rho = r - S - 1;                        // residual row
+                const double2 c = mid[S];
+                double2 res = make_double2(0.0, 0.0);             // 0 on the boundary (:559)
+                if (rho > 0 && rho < N - 1) {
+                    const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
+                    if (x_in) res.x = residual_fast(c.x, sum4(x.x, lo[S].x, c.y, left), fw[S].x, inv_h2);
+                    if (y_in) res.y = residual_fast(c.y, sum4(x.y, lo[S].y, right, c.x), fw[S].y, inv_h2);
+                    if (ERR && rho >= own_r_lo && rho < own_r_hi && col_own) {
+                        // red = (row + column) even: exactly one of the lane's two columns (:609-611)
+                        const double v = ((rho + cx) & 1) ? res.y : res.x;
+                        err_acc = __dadd_rn(err_acc, fabs(v));
+                    }
+                }
+                lo[S] = c;
+                mid[S] = x;
+                if (RES) {
+                    const double2 d_cur = make_double2(-res.x, -res.y);   // D = -D (:277-280)
+                    const int f_row = rho - 1;                            // lower fine row of the pair (f_row, rho)
+                    if (f_row >= own_r_lo && f_row < own_r_hi) {
+                        const int crow = p.f2c[f_row];
+                        if (crow >= 0) {
+                            const double cw = p.rw[crow];
+                            const double np = shfl_dn1(d_prev.x), nc = shfl_dn1(d_cur.x);
+                            const bool row_edge = crow == 0 || crow == p.M - 1;
+                            if (ccx >= 0) {
+                                const bool edge = row_edge || ccx == 0 || ccx == p.M - 1;
+                                p.Fc[(size_t)crow * p.M + ccx] = edge ? 0.0 : restrict_at(d_prev.x, d_prev.y, d_cur.x, d_cur.y, ax, cw);
+                            }
+                            if (ccy >= 0) {
+                                const bool edge = row_edge || ccy == 0 || ccy == p.M - 1;
+                                p.Fc[(size_t)crow * p.M + ccy] = edge ? 0.0 : restrict_at(d_prev.y, np, d_cur.y, nc, ay, cw);
+                            }
+                        }
+                    }
+                    d_prev = d_cur;
+                }
+            }
+        }
+    }
+
+    if (ERR) {
+        __shared__ double red_smem[32];
+        __shared__ bool is_last;
+        const double total = block_sum<STREAM_WARPS * 32>(err_acc, red_smem);
+        if (threadIdx.x == 0) {
+            p.partials[blockIdx.x] = total;
+            __threadfence();
+            is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        double s = 0.0;
+        for (unsigned k = threadIdx.x; k < gridDim.x; k += STREAM_WARPS * 32) s = __dadd_rn(s, __ldcg(&p.partials[k]));
+        s = block_sum<STREAM_WARPS * 32>(s, red_smem);
+        if (threadIdx.x == 0) {
+            double e = __dadd_rn(s, s);                           // sum1 + sum2 over the same parity (:621)
+            e = __ddiv_rn(e, (double)N);
+            e = __ddiv_rn(e, (double)N);
+            if (p.err_dev) *p.err_dev = e;
+            if (p.err_slot) { *p.err_slot = e; __threadfence_system(); }
+            *p.counter = 0u;
+        }
+    }
+}
+
+}  // namespace mg
