@@ -245,7 +245,7 @@ void doSmoothing(int N, double L, double *U, double *F, int step, double *error)
     Context &c = ctx();
     double *work = scratch_grid((size_t)N * N);
     if (!work) return;
-    double *res = smooth_out_of_place(N, L, U, work, F, step, false, c.dev_scalar, nullptr);
+    double *res = smooth_out_of_place(N, L, U, work, U, F, step, false, c.dev_scalar, nullptr);
     if (res != U) mgGridCopy(N, U, res);
     if (error) {
         check(cudaMemcpyAsync(error, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H error");
@@ -313,18 +313,18 @@ double mgAnalyticError(int N, double L, const double *U, double min_x, double mi
 void mgSmooth(int N, double L, const double *U_in, double *F, int step, double *U_out, double *error_slot)
 {
     if (!ensure_ready()) return;
-    // out-of-place contract: U_in is left untouched, so odd/even sweep counts use the scratch grid as partner
+    // out-of-place contract: U_in is never written; the passes alternate between U_out and a
+    // scratch grid, ordered so that the last one lands in U_out
     Context &c = ctx();
     double *err_dev = error_slot ? c.dev_scalar : nullptr;
-    if (step == 1) {
-        smooth_out_of_place(N, L, const_cast<double *>(U_in), U_out, F, 1, false, err_dev, slot_device_ptr(error_slot));
-        return;
-    }
-    double *work = scratch_grid((size_t)N * N);
-    if (!work) return;
-    mgGridCopy(N, work, U_in);
-    double *res = smooth_out_of_place(N, L, work, U_out, F, step, false, err_dev, slot_device_ptr(error_slot));
-    if (res != U_out) mgGridCopy(N, U_out, res);
+    const int passes = smooth_pass_count(N, step);
+    if (passes == 0) mgGridCopy(N, U_out, U_in);
+    double *work = passes > 1 ? scratch_grid((size_t)N * N) : nullptr;
+    if (passes > 1 && !work) return;
+    const double *in = passes == 0 ? U_out : U_in;
+    double *a = (passes % 2) ? U_out : work, *b = (passes % 2) ? work : U_out;
+    double *res = smooth_out_of_place(N, L, in, a, b, F, step, false, err_dev, slot_device_ptr(error_slot));
+    if (passes > 0 && res != U_out) fail(-8, "mgSmooth: internal pass parity error");
 }
 
 double *mgDownLeg(int N, double L, double *U, double *U_work, double *F, int step, int zero_init, int M, double *F_c,

@@ -82,7 +82,13 @@ void launch_stream(StreamParams &p)
         p.partials = partials_buf(blocks);
         p.counter = c.counters;
     }
-    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, 0, c.stream>>>(p);
+    static bool opted_in = false;   // one flag per instantiation
+    if (!opted_in) {
+        check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES),
+              "cudaFuncSetAttribute(k_stream)");
+        opted_in = true;
+    }
+    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, STREAM_SMEM_BYTES, c.stream>>>(p);
     c.launches++;
     check(cudaGetLastError(), "k_stream");
 }
@@ -140,14 +146,17 @@ struct LegSpec {
     double *err_dev = nullptr, *err_slot = nullptr;
 };
 
-// Runs the passes of one leg on even N.  `a` holds the input of the first pass (unless IN_ZERO),
-// `b` is the ping-pong partner.  Returns the buffer holding the final level.
-double *run_leg(int N, double L, double *a, double *b, const double *F, int step, const LegSpec &spec)
+// Runs the passes of one leg on even N.  The first pass reads `in` (never written, unused for
+// IN_ZERO); the passes write alternately to `a`, `b`, `a`, ...  Returns the buffer holding the
+// final level (`in` itself if no pass produced a new level).
+double *run_leg(int N, double L, const double *in, double *a, double *b, const double *F, int step, const LegSpec &spec)
 {
     const Spacing sp = spacing(N, L);
     std::vector<int> passes = split_passes(step);
     if (passes.empty()) passes.push_back(0);   // a pass without sweeps (prolong-add only / residual+restrict only)
-    double *src = a, *dst = b;
+    const double *src = in;
+    double *bufs[2] = {a, b};
+    int next = 0;
     for (size_t k = 0; k < passes.size(); ++k) {
         const bool first = k == 0, last = k + 1 == passes.size();
         StreamParams p{};
@@ -155,10 +164,9 @@ double *run_leg(int N, double L, double *a, double *b, const double *F, int step
         p.h2 = sp.h2;
         p.inv_h2 = sp.inv_h2;
         p.F = F;
-        const int in = first ? spec.in : IN_LOAD;
+        const int in_mode = first ? spec.in : IN_LOAD;
         p.Uin = src;
-        // An IN_ZERO pass reads nothing, so it may write straight into `a`.
-        double *out = (in == IN_ZERO) ? src : dst;
+        double *out = bufs[next];
         p.Uout = out;
         int mode = 0;
         if (last && spec.want_res) mode = 2;
@@ -174,7 +182,7 @@ double *run_leg(int N, double L, double *a, double *b, const double *F, int step
             p.f2c = t.f2c;
             p.rw = t.rw;
         }
-        if (in == IN_PROLONG) {
+        if (in_mode == IN_PROLONG) {
             const ProlongTable &t = prolong_table(spec.Nc, N);
             p.Nc = spec.Nc;
             p.Uc = spec.Uc;
@@ -185,17 +193,18 @@ double *run_leg(int N, double L, double *a, double *b, const double *F, int step
             p.c_dx = 1.0 / (double)(spec.Nc - 1);
             p.inv_c_dx = 1.0 / p.c_dx;
         }
-        if (passes[k] == 0 && in == IN_LOAD && mode == 0) break;   // nothing to do
-        if (passes[k] == 0 && in == IN_LOAD) {
+        if (passes[k] == 0 && in_mode == IN_LOAD && mode == 0) break;   // nothing to do
+        if (passes[k] == 0 && in_mode == IN_LOAD) {
             // residual / restriction of the input itself: no new level is produced, keep `src`
             p.Uout = nullptr;   // level S is the input itself: nothing to write
-            launch_stream_any(0, in, mode, p);
+            launch_stream_any(0, in_mode, mode, p);
             continue;
         }
-        launch_stream_any(passes[k], in, mode, p);
-        if (out == dst) std::swap(src, dst);
+        launch_stream_any(passes[k], in_mode, mode, p);
+        src = out;
+        next ^= 1;
     }
-    return src;
+    return const_cast<double *>(src);
 }
 
 }  // namespace
@@ -206,32 +215,39 @@ void fused_init()
     if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
 }
 
-double *smooth_out_of_place(int N, double L, double *a, double *b, const double *F, int step, bool in_is_zero,
-                            double *err_dev, double *err_slot)
+int smooth_pass_count(int N, int step)
+{
+    if (step <= 0) return 0;
+    return streamable(N) ? (step + STREAM_SMAX - 1) / STREAM_SMAX : step;
+}
+
+double *smooth_out_of_place(int N, double L, const double *in, double *a, double *b, const double *F, int step,
+                            bool in_is_zero, double *err_dev, double *err_slot)
 {
     const bool want_err = err_dev || err_slot;
+    if (step == 0 && in_is_zero) {
+        check(cudaMemsetAsync(a, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
+        in = a;
+        std::swap(a, b);
+    }
     if (streamable(N) && (step > 0 || want_err)) {
-        if (step == 0 && in_is_zero) check(cudaMemsetAsync(a, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
         LegSpec spec;
         spec.in = (in_is_zero && step > 0) ? IN_ZERO : IN_LOAD;
         spec.want_err = want_err;
         spec.err_dev = err_dev;
         spec.err_slot = err_slot;
-        return run_leg(N, L, a, b, F, step, spec);
+        return run_leg(N, L, in, a, b, F, step, spec);
     }
     const Spacing sp = spacing(N, L);
-    double *cur = a, *other = b;
+    const double *cur = in;
+    double *bufs[2] = {a, b};
     for (int s = 0; s < step; ++s) {
-        if (s == 0 && in_is_zero) {
-            launch_sweep(N, sp.h2, cur, F, cur, true);  // the input is implied zeros: safe in place
-        } else {
-            launch_sweep(N, sp.h2, cur, F, other, false);
-            std::swap(cur, other);
-        }
+        double *out = bufs[s & 1];
+        launch_sweep(N, sp.h2, cur, F, out, s == 0 && in_is_zero);
+        cur = out;
     }
-    if (step == 0 && in_is_zero) check(cudaMemsetAsync(cur, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
     if (want_err) launch_smooth_error(N, sp.inv_h2, cur, F, err_dev, err_slot);
-    return cur;
+    return const_cast<double *>(cur);
 }
 
 double *down_leg(int N, double L, double *U, double *U_work, const double *F, int step, bool zero_init, int M,
@@ -247,10 +263,10 @@ double *down_leg(int N, double L, double *U, double *U_work, const double *F, in
         spec.Fc = F_c;
         spec.err_dev = step > 0 ? ctx().dev_scalar : nullptr;
         spec.err_slot = step > 0 ? err_slot : nullptr;
-        return run_leg(N, L, U, U_work, F, step, spec);
+        return run_leg(N, L, U, U_work, U, F, step, spec);
     }
     const Spacing sp = spacing(N, L);
-    double *res = smooth_out_of_place(N, L, U, U_work, F, step, zero_init, step > 0 ? ctx().dev_scalar : nullptr,
+    double *res = smooth_out_of_place(N, L, U, U_work, U, F, step, zero_init, step > 0 ? ctx().dev_scalar : nullptr,
                                       step > 0 ? err_slot : nullptr);
     double *D = scratch_grid((size_t)N * N);
     if (!D) return res;
@@ -271,11 +287,11 @@ double *up_leg(int Nc, const double *U_c, int N, double L, double *U_f, double *
         spec.want_err = step > 0;
         spec.err_dev = step > 0 ? ctx().dev_scalar : nullptr;
         spec.err_slot = step > 0 ? err_slot : nullptr;
-        return run_leg(N, L, U_f, U_work, F, step > 0 ? step : 0, spec);
+        return run_leg(N, L, U_f, U_work, U_f, F, step > 0 ? step : 0, spec);
     }
     launch_prolong(Nc, U_c, N, U_f, U_f);
     if (step <= 0) return U_f;
-    return smooth_out_of_place(N, L, U_f, U_work, F, step, false, ctx().dev_scalar, err_slot);
+    return smooth_out_of_place(N, L, U_f, U_work, U_f, F, step, false, ctx().dev_scalar, err_slot);
 }
 
 }  // namespace mg

@@ -38,6 +38,8 @@ enum { IN_LOAD = 0, IN_ZERO = 1, IN_PROLONG = 2 };
 
 constexpr int STREAM_WARPS = 8;         // warps (= strips) per CTA
 constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
+constexpr int STREAM_DEPTH = 8;         // rows in flight per warp (cp.async ring in shared memory), power of two
+constexpr int STREAM_SMEM_BYTES = STREAM_WARPS * STREAM_DEPTH * 2 * 32 * 16;   // [warp][slot][U|F][lane] x 16 B
 
 struct StreamParams {
     int N;                  // grid size (even)
@@ -99,16 +101,41 @@ __device__ __forceinline__ double residual_fast(double u, double s4, double f, d
 }
 
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+
+// 16-byte asynchronous global->shared copy (LDGSTS); !valid zero-fills the destination.
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gsrc, bool valid)
+{
+    const int src_bytes = valid ? 16 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+__device__ __forceinline__ double2 lds2(unsigned smem_addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <bool B>
+struct BoolTag { static constexpr bool value = B; };
 
 template <int S, int IN, bool ERR, bool RES>
 __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamParams p)
 {
     constexpr bool NEED_R = ERR || RES;
     using G = StreamGeo<S, NEED_R, RES>;
-    constexpr int NF = S + (NEED_R ? 1 : 0);     // F rows kept: fw[k] = F row (r-1-k)
-    constexpr int NL = S + (NEED_R ? 1 : 0);     // levels that keep a two-row window
+    constexpr int NLV = S + (NEED_R ? 1 : 0);    // levels that keep a two-row window (level t feeds stage t)
+    constexpr int NF = NLV;                      // F rows alive at once: rows r-1 ... r-NF
+    constexpr int NR = NF <= 2 ? 2 : 4;          // F ring size; also the unroll factor (even: the row windows have period 2)
+    constexpr int U = NR;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N;
@@ -117,10 +144,12 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     const bool active = strip < p.n_strips;
 
     const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
-    const int cx = own_c_lo - G::HL + 2 * lane;                 // this lane's columns: cx, cx+1 (cx even)
+    const int c_first = own_c_lo - G::HL;                       // first column of the 64-wide window (even)
+    const int cx = c_first + 2 * lane;                          // this lane's columns: cx, cx+1
     const bool col_ok = active && cx >= 0 && cx < N;            // N even => cx+1 < N too
     const bool col_own = col_ok && cx >= own_c_lo && cx < own_c_hi;
     const bool x_in = cx > 0, y_in = cx + 1 < N - 1;            // interior columns
+    const bool strip_fast = c_first >= 1 && c_first + 63 <= N - 2;   // every column of the window is interior
     const int own_r_lo = seg * p.H, own_r_hi = min(own_r_lo + p.H, N);
     const int r_first = max(0, own_r_lo - G::ROW_LEAD);
     const int r_last = active ? min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD) : -1;   // idle warps skip the loop
@@ -128,12 +157,25 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     const double h2 = p.h2, inv_h2 = p.inv_h2;
     const double *__restrict__ Fp = p.F;
     const double *__restrict__ Up = p.Uin;
+    double *__restrict__ Op = p.Uout;
+    const ptrdiff_t ldn = N;
 
-    double2 lo[NL > 0 ? NL : 1], mid[NL > 0 ? NL : 1], fw[NF > 0 ? NF : 1];
+    // Register state.  Every index below is a compile-time constant after unrolling, so the
+    // arrays live in registers and rotate by renaming, not by moves.
+    double2 w[NLV > 0 ? NLV : 1][2];             // w[t][slot]: the two newest rows of level t
+    double2 fr[NR];                              // F ring: the row that arrives at in-chunk step k sits in fr[k % NR]
 #pragma unroll
-    for (int t = 0; t < (NL > 0 ? NL : 1); ++t) lo[t] = mid[t] = make_double2(0.0, 0.0);
+    for (int t = 0; t < (NLV > 0 ? NLV : 1); ++t) w[t][0] = w[t][1] = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int t = 0; t < (NF > 0 ? NF : 1); ++t) fw[t] = make_double2(0.0, 0.0);
+    for (int t = 0; t < NR; ++t) fr[t] = make_double2(0.0, 0.0);
+
+    // Streamed rows are staged through a per-warp ring in shared memory filled by cp.async:
+    // STREAM_DEPTH rows of U and F in flight per warp at no register cost.  Each lane copies
+    // and later reads back only its own 16 bytes, so no barrier is involved, only wait_group.
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    constexpr int SLOT_BYTES = 2 * 32 * 16;      // [U|F][lane] x 16 B
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_DEPTH * SLOT_BYTES) + lane * 16;
+    unsigned slot_off = 0;                       // byte offset of the slot that holds the row of the current step
 
     // ---- restriction state
     double2 d_prev = make_double2(0.0, 0.0);
@@ -156,34 +198,50 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     }
     double err_acc = 0.0;
 
-    // ---- two-deep register prefetch of the streamed rows
-    double2 pu[2], pf[2];
-    auto fetch = [&](int r, double2 &u, double2 &f) {
-        u = make_double2(0.0, 0.0);
-        f = make_double2(0.0, 0.0);
-        if (!col_ok) return;
-        if (IN != IN_ZERO && r <= N - 1) u = ld2(Up + (size_t)r * N + cx);
-        if (NF > 0 && r >= 1 && r <= N) f = ld2(Fp + (size_t)(r - 1) * N + cx);   // F row r-1 is first used at step r
+    // guarded issue of level-0 row r and of F row r-1 (first used at step r) into ring slot `off`
+    auto issue = [&](int r, unsigned off) {
+        if (IN != IN_ZERO) {
+            const bool ok = col_ok && r <= N - 1;
+            cp_async16(ring_base + off, ok ? (const void *)(Up + (ptrdiff_t)r * ldn + cx) : (const void *)Up, ok);
+        }
+        if (NF > 0) {
+            const bool ok = col_ok && r >= 1 && r <= N;
+            cp_async16(ring_base + off + 512, ok ? (const void *)(Fp + (ptrdiff_t)(r - 1) * ldn + cx) : (const void *)Fp, ok);
+        }
+        cp_async_commit();
     };
-    fetch(r_first, pu[0], pf[0]);
-    fetch(r_first + 1, pu[1], pf[1]);
-
-    for (int rb = r_first; rb <= r_last; rb += 2) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+    for (int d = 0; d < STREAM_DEPTH; ++d) issue(r_first + d, d * SLOT_BYTES);
+
+    // One chunk = U consecutive steps.  FAST: every row touched by every stage is an interior
+    // row, every column of the window is an interior column and all loads are in range, so the
+    // body carries no boundary selects at all.
+    auto chunk = [&](auto fast_tag, const int rb) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
             const int r = rb + k;
-            if (r > r_last) break;
-            double2 x = pu[k];
-            const double2 f_new = pf[k];
-            fetch(r + 2, pu[k], pf[k]);
+            cp_async_wait<STREAM_DEPTH - 1>();                    // the group of row r has landed
+            double2 x = make_double2(0.0, 0.0), f_new = x;
+            if (IN != IN_ZERO) x = lds2(ring_base + slot_off);
+            if (NF > 0) f_new = lds2(ring_base + slot_off + 512);
+            // refill the slot with row r + DEPTH (the values above are in registers by now)
+            if (FAST) {
+                if (IN != IN_ZERO) cp_async16(ring_base + slot_off, Up + (ptrdiff_t)(r + STREAM_DEPTH) * ldn + cx);
+                if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
+                cp_async_commit();
+            } else {
+                issue(r + STREAM_DEPTH, slot_off);
+            }
+            slot_off = (slot_off + SLOT_BYTES) & (STREAM_DEPTH * SLOT_BYTES - 1);
 
             // ---- level 0 of the 1 node: U_f + P(U_c)
-            if (IN == IN_PROLONG && r <= N - 1) {
+            if (IN == IN_PROLONG && (FAST || r <= N - 1)) {
                 const int rq = p.row_cell[r];
                 const double2 wr = p.row_w[r];
                 if (rq != prev_rq) {
                     const double *c_lo = p.Uc + (size_t)rq * p.Nc, *c_hi = c_lo + p.Nc;
-                    if (col_ok) {
+                    if (FAST || col_ok) {
                         if (rq == prev_rq + 1) bot = top;
                         else {
                             bot.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
@@ -200,49 +258,52 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
                 x.y = __dadd_rn(x.y, div_by_invariant(div_by_invariant(vy, p.c_dx, p.inv_c_dx), p.c_dx, p.inv_c_dx));
             }
 
-            // ---- shift the F window
-#pragma unroll
-            for (int t = NF - 1; t > 0; --t) fw[t] = fw[t - 1];
-            if (NF > 0) fw[0] = f_new;
+            if (NF > 0) fr[k % NR] = f_new;
 
-            // ---- S sweeps: level t row (r-t-1) -> level t+1
+            // ---- S sweeps: stage t turns level t row (r-t-1) into level t+1
 #pragma unroll
             for (int t = 0; t < S; ++t) {
                 const int i = r - t - 1;
-                const double2 c = mid[t];
-                double2 nx = c;                                   // boundary rows/columns are carried over
-                if (i > 0 && i < N - 1) {
-                    const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
-                    if (x_in) nx.x = jacobi_fast(c.x, sum4(x.x, lo[t].x, c.y, left), __dmul_rn(h2, fw[t].x));
-                    if (y_in) nx.y = jacobi_fast(c.y, sum4(x.y, lo[t].y, right, c.x), __dmul_rn(h2, fw[t].y));
+                const double2 below = w[t][k & 1], c = w[t][(k & 1) ^ 1];
+                const double2 f = fr[(k - t + 4 * NR) % NR];
+                const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
+                double2 nx;
+                nx.x = jacobi_fast(c.x, sum4(x.x, below.x, c.y, left), __dmul_rn(h2, f.x));
+                nx.y = jacobi_fast(c.y, sum4(x.y, below.y, right, c.x), __dmul_rn(h2, f.y));
+                if (!FAST) {                                      // boundary rows / columns are carried over
+                    const bool row_in = i > 0 && i < N - 1;
+                    nx.x = (row_in && x_in) ? nx.x : c.x;
+                    nx.y = (row_in && y_in) ? nx.y : c.y;
                 }
-                lo[t] = c;
-                mid[t] = x;
+                w[t][k & 1] = x;
                 x = nx;
             }
 
             // ---- x is now level S, row r-S
             {
                 const int i = r - S;
-                if (p.Uout && i >= own_r_lo && i < own_r_hi && col_own) *reinterpret_cast<double2 *>(p.Uout + (size_t)i * N + cx) = x;
+                if (Op && i >= own_r_lo && i < own_r_hi && col_own) *reinterpret_cast<double2 *>(Op + (ptrdiff_t)i * ldn + cx) = x;
             }
 
             if (NEED_R) {
                 const int rho = r - S - 1;                        // residual row
-                const double2 c = mid[S];
-                double2 res = make_double2(0.0, 0.0);             // 0 on the boundary (:559)
-                if (rho > 0 && rho < N - 1) {
-                    const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
-                    if (x_in) res.x = residual_fast(c.x, sum4(x.x, lo[S].x, c.y, left), fw[S].x, inv_h2);
-                    if (y_in) res.y = residual_fast(c.y, sum4(x.y, lo[S].y, right, c.x), fw[S].y, inv_h2);
-                    if (ERR && rho >= own_r_lo && rho < own_r_hi && col_own) {
-                        // red = (row + column) even: exactly one of the lane's two columns (:609-611)
-                        const double v = ((rho + cx) & 1) ? res.y : res.x;
-                        err_acc = __dadd_rn(err_acc, fabs(v));
-                    }
+                const double2 below = w[S][k & 1], c = w[S][(k & 1) ^ 1];
+                const double2 f = fr[(k - S + 4 * NR) % NR];
+                const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
+                double2 res;
+                res.x = residual_fast(c.x, sum4(x.x, below.x, c.y, left), f.x, inv_h2);
+                res.y = residual_fast(c.y, sum4(x.y, below.y, right, c.x), f.y, inv_h2);
+                if (!FAST) {                                      // 0 on the boundary (:559)
+                    const bool row_in = rho > 0 && rho < N - 1;
+                    res.x = (row_in && x_in) ? res.x : 0.0;
+                    res.y = (row_in && y_in) ? res.y : 0.0;
                 }
-                lo[S] = c;
-                mid[S] = x;
+                w[S][k & 1] = x;
+                if (ERR) {
+                    // red = (row + column) even: exactly one of the lane's two columns (:609-611)
+                    const double v = (rho & 1) ? res.y : res.x;   // cx is even
+                    if (rho >= own_r_lo && rho < own_r_hi && col_own) err_acc = __dadd_rn(err_acc, fabs(v));
+                }
                 if (RES) {
                     const double2 d_cur = make_double2(-res.x, -res.y);   // D = -D (:277-280)
                     const int f_row = rho - 1;                            // lower fine row of the pair (f_row, rho)
@@ -266,8 +327,15 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
                 }
             }
         }
+    };
+
+    for (int rb = r_first; rb <= r_last; rb += U) {
+        const bool fast = strip_fast && rb - NLV >= 1 && rb + U - 1 + STREAM_DEPTH <= N - 1;
+        if (fast) chunk(BoolTag<true>(), rb);
+        else chunk(BoolTag<false>(), rb);
     }
 
+    cp_async_wait<0>();
     if (ERR) {
         __shared__ double red_smem[32];
         __shared__ bool is_last;
