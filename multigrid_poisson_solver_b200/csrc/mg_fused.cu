@@ -18,6 +18,7 @@ struct FusedRestrictTable {
     bool usable = false;
     int *f2c = nullptr;     // device [N]
     double *rw = nullptr;   // device [M]
+    double2 *rrow = nullptr;  // device [N]: {coarse row or -1, its weight}
 };
 std::map<std::pair<int, int>, FusedRestrictTable> g_restrict_tables;
 int g_force_H = 0;
@@ -47,7 +48,11 @@ const FusedRestrictTable &fused_restrict_table(int N, int M)
         if (ok && f2c[0] == -1 && f2c[N - 2] == -1) {
             f2c[0] = 0;
             f2c[N - 2] = M - 1;
+            std::vector<double2> rrow((size_t)N);
+            for (int f = 0; f < N; ++f) rrow[f] = make_double2((double)f2c[f], f2c[f] >= 0 ? rw[f2c[f]] : 0.0);
             bool good = check(cudaMalloc(&t.f2c, (size_t)N * sizeof(int)), "cudaMalloc f2c");
+            good = good && check(cudaMalloc(&t.rrow, (size_t)N * sizeof(double2)), "cudaMalloc rrow");
+            good = good && check(cudaMemcpy(t.rrow, rrow.data(), (size_t)N * sizeof(double2), cudaMemcpyHostToDevice), "H2D rrow");
             good = good && check(cudaMalloc(&t.rw, (size_t)M * sizeof(double)), "cudaMalloc rw");
             // synchronous copies from pageable memory: the vectors die at the end of this scope
             good = good && check(cudaMemcpy(t.f2c, f2c.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice), "H2D f2c");
@@ -84,11 +89,11 @@ void launch_stream(StreamParams &p)
     }
     static bool opted_in = false;   // one flag per instantiation
     if (!opted_in) {
-        check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES),
+        check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem_bytes(IN)),
               "cudaFuncSetAttribute(k_stream)");
         opted_in = true;
     }
-    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, STREAM_SMEM_BYTES, c.stream>>>(p);
+    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, stream_smem_bytes(IN), c.stream>>>(p);
     c.launches++;
     check(cudaGetLastError(), "k_stream");
 }
@@ -181,6 +186,7 @@ double *run_leg(int N, double L, const double *in, double *a, double *b, const d
             p.Fc = spec.Fc;
             p.f2c = t.f2c;
             p.rw = t.rw;
+            p.rrow = t.rrow;
         }
         if (in_mode == IN_PROLONG) {
             const ProlongTable &t = prolong_table(spec.Nc, N);
@@ -279,7 +285,8 @@ double *down_leg(int N, double L, double *U, double *U_work, const double *F, in
 double *up_leg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, const double *F, int step,
                double *err_slot)
 {
-    if (streamable(N) && Nc >= 2) {
+    // a 64-column window must map into at most 62 coarse cells (the staged part of a coarse row)
+    if (streamable(N) && Nc >= 2 && (double)(N - 1) >= 1.2 * (double)(Nc - 1)) {
         LegSpec spec;
         spec.in = IN_PROLONG;
         spec.Nc = Nc;

@@ -39,7 +39,9 @@ enum { IN_LOAD = 0, IN_ZERO = 1, IN_PROLONG = 2 };
 constexpr int STREAM_WARPS = 8;         // warps (= strips) per CTA
 constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
 constexpr int STREAM_DEPTH = 8;         // rows in flight per warp (cp.async ring in shared memory), power of two
-constexpr int STREAM_SMEM_BYTES = STREAM_WARPS * STREAM_DEPTH * 2 * 32 * 16;   // [warp][slot][U|F][lane] x 16 B
+// shared memory: [warp][slot][U | F (| coarse row, 1 node only)][lane] x 16 B
+__host__ __device__ constexpr int stream_slot_bytes(int in) { return (in == 2 ? 3 : 2) * 32 * 16; }
+__host__ __device__ constexpr int stream_smem_bytes(int in) { return STREAM_WARPS * STREAM_DEPTH * stream_slot_bytes(in); }
 
 struct StreamParams {
     int N;                  // grid size (even)
@@ -58,6 +60,7 @@ struct StreamParams {
     double *Fc;
     const int *f2c;         // [N]  fine index -> coarse index whose lower-left fine point it is, or -1
     const double *rw;       // [M]  fmod weight of the coarse index
+    const double2 *rrow;    // [N]  per fine row: {coarse row (as a double) or -1, its fmod weight}
     // IN_PROLONG
     int Nc;
     const double *Uc;
@@ -88,6 +91,21 @@ __device__ __forceinline__ double div_by_invariant(double x, double d, double y)
     return __fma_rn(r1, y, q1);
 }
 
+// The same quotient without the range test (callers test div_unsafe and redo the rare cases).
+__device__ __forceinline__ double div_fast(double x, double d, double y)
+{
+    const double q0 = __dmul_rn(x, y);
+    const double r0 = __fma_rn(-q0, d, x);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-q1, d, x);
+    return __fma_rn(r1, y, q1);
+}
+__device__ __forceinline__ bool div_unsafe(double x)
+{
+    const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+    return e - 200u > 1600u;                       // zero, subnormal, huge, inf, nan
+}
+
 // s4 - 4*u with one rounding == the reference's (s4 - RN(4*u)) because 4*u is exact.
 __device__ __forceinline__ double sub4(double s4, double u) { return __fma_rn(-4.0, u, s4); }
 
@@ -111,6 +129,18 @@ __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gsrc,
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+// 8-byte variant (coarse rows of odd length are only 8-byte aligned)
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void *gsrc, bool valid)
+{
+    const int src_bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ double lds1(unsigned smem_addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_PENDING>
@@ -173,33 +203,51 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     // STREAM_DEPTH rows of U and F in flight per warp at no register cost.  Each lane copies
     // and later reads back only its own 16 bytes, so no barrier is involved, only wait_group.
     extern __shared__ __align__(16) unsigned char stream_smem[];
-    constexpr int SLOT_BYTES = 2 * 32 * 16;      // [U|F][lane] x 16 B
-    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_DEPTH * SLOT_BYTES) + lane * 16;
+    constexpr int SLOT_BYTES = stream_slot_bytes(IN);   // [U | F | coarse row][lane] x 16 B
+    const unsigned warp_ring = (unsigned)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_DEPTH * SLOT_BYTES);
+    const unsigned ring_base = warp_ring + lane * 16;
     unsigned slot_off = 0;                       // byte offset of the slot that holds the row of the current step
 
     // ---- restriction state
     double2 d_prev = make_double2(0.0, 0.0);
     int ccx = -1, ccy = -1;
     double ax = 0.0, ay = 0.0;
+    bool zx = true, zy = true;                   // coarse column on the coarse boundary: value forced to 0
+    double2 rinfo_next = make_double2(-1.0, 0.0);   // {coarse row, weight} of the fine row the NEXT step pairs up
     if (RES && col_own) {
         ccx = p.f2c[cx];
         ccy = p.f2c[cx + 1];
         if (ccx >= 0) ax = p.rw[ccx];
         if (ccy >= 0) ay = p.rw[ccy];
+        zx = ccx == 0 || ccx == p.M - 1;
+        zy = ccy == 0 || ccy == p.M - 1;
+    }
+    if (RES && active) {
+        const int f0 = r_first - S - 2;           // the fine row step r_first pairs with the one above it
+        if (f0 >= 0 && f0 <= N - 1) rinfo_next = p.rrow[f0];
     }
     // ---- prolongation state
-    int cqx = 0, cqy = 0, prev_rq = -4;
-    double2 wcx = make_double2(0.0, 0.0), wcy = wcx, bot = wcx, top = wcx;
-    if (IN == IN_PROLONG && col_ok) {
-        cqx = p.col_cell[cx];
-        cqy = p.col_cell[cx + 1];
-        wcx = p.col_w[cx];
-        wcy = p.col_w[cx + 1];
+    // Coarse rows are staged through the third part of each ring slot: the slot of fine row r
+    // holds doubles [cbase, cbase+64) of coarse row row_cell[r]+1 (the upper row of its cell).
+    int cqx = 0, cqy = 0, prev_rq = -4, cbase = 0, rq_next = 0, rq_ahead = 0;
+    unsigned ox = 0, oy = 0;                     // byte offsets of this lane's two cells inside a staged coarse row
+    double2 wcx = make_double2(0.0, 0.0), wcy = wcx, bot = wcx, top = wcx, wr_next = wcx;
+    if (IN == IN_PROLONG) {
+        if (col_ok) {
+            cqx = p.col_cell[cx];
+            cqy = p.col_cell[cx + 1];
+            wcx = p.col_w[cx];
+            wcy = p.col_w[cx + 1];
+        }
+        cbase = __reduce_min_sync(0xffffffffu, col_ok ? cqx : 0x7fffffff) & ~1;
+        ox = col_ok ? (unsigned)(cqx - cbase) * 8u : 0u;     // lanes outside the grid read slot element 0 (unused)
+        oy = col_ok ? (unsigned)(cqy - cbase) * 8u : 0u;
     }
     double err_acc = 0.0;
 
-    // guarded issue of level-0 row r and of F row r-1 (first used at step r) into ring slot `off`
-    auto issue = [&](int r, unsigned off) {
+    // guarded issue of level-0 row r and of F row r-1 (first used at step r) into ring slot `off`;
+    // for the 1 node also the upper coarse row of fine row r's cell (`rq` = row_cell[r])
+    auto issue = [&](int r, unsigned off, int rq) {
         if (IN != IN_ZERO) {
             const bool ok = col_ok && r <= N - 1;
             cp_async16(ring_base + off, ok ? (const void *)(Up + (ptrdiff_t)r * ldn + cx) : (const void *)Up, ok);
@@ -208,10 +256,34 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
             const bool ok = col_ok && r >= 1 && r <= N;
             cp_async16(ring_base + off + 512, ok ? (const void *)(Fp + (ptrdiff_t)(r - 1) * ldn + cx) : (const void *)Fp, ok);
         }
+        if (IN == IN_PROLONG) {
+            const int c0 = cbase + 2 * lane;
+            const bool row_ok = active && r <= N - 1;
+            const double *src = p.Uc + (size_t)(row_ok ? rq + 1 : 0) * p.Nc + c0;
+            const bool ok0 = row_ok && c0 < p.Nc, ok1 = row_ok && c0 + 1 < p.Nc;
+            cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.Uc, ok0);
+            cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.Uc, ok1);
+        }
         cp_async_commit();
     };
 #pragma unroll
-    for (int d = 0; d < STREAM_DEPTH; ++d) issue(r_first + d, d * SLOT_BYTES);
+    for (int d = 0; d < STREAM_DEPTH; ++d) {
+        int rq = 0;
+        if (IN == IN_PROLONG && active && r_first + d <= N - 1) rq = p.row_cell[r_first + d];
+        issue(r_first + d, d * SLOT_BYTES, rq);
+    }
+    if (IN == IN_PROLONG && active) {
+        rq_next = p.row_cell[r_first];
+        wr_next = p.row_w[r_first];
+        if (r_first + STREAM_DEPTH <= N - 1) rq_ahead = p.row_cell[r_first + STREAM_DEPTH];
+        // lower coarse row of the first cell: the only one that is not staged
+        const double *c_lo = p.Uc + (size_t)rq_next * p.Nc;
+        if (col_ok) {
+            top.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
+            top.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
+        }
+        prev_rq = rq_next - 1;                    // so that the first step shifts `top` down and loads the upper row
+    }
 
     // One chunk = U consecutive steps.  FAST: every row touched by every stage is an interior
     // row, every column of the window is an interior column and all loads are in range, so the
@@ -225,38 +297,57 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
             double2 x = make_double2(0.0, 0.0), f_new = x;
             if (IN != IN_ZERO) x = lds2(ring_base + slot_off);
             if (NF > 0) f_new = lds2(ring_base + slot_off + 512);
-            // refill the slot with row r + DEPTH (the values above are in registers by now)
-            if (FAST) {
-                if (IN != IN_ZERO) cp_async16(ring_base + slot_off, Up + (ptrdiff_t)(r + STREAM_DEPTH) * ldn + cx);
-                if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
-                cp_async_commit();
-            } else {
-                issue(r + STREAM_DEPTH, slot_off);
-            }
-            slot_off = (slot_off + SLOT_BYTES) & (STREAM_DEPTH * SLOT_BYTES - 1);
 
-            // ---- level 0 of the 1 node: U_f + P(U_c)
-            if (IN == IN_PROLONG && (FAST || r <= N - 1)) {
-                const int rq = p.row_cell[r];
-                const double2 wr = p.row_w[r];
-                if (rq != prev_rq) {
-                    const double *c_lo = p.Uc + (size_t)rq * p.Nc, *c_hi = c_lo + p.Nc;
-                    if (FAST || col_ok) {
-                        if (rq == prev_rq + 1) bot = top;
-                        else {
-                            bot.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
-                            bot.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
-                        }
-                        top.x = __dadd_rn(__dmul_rn(c_hi[cqx], wcx.x), __dmul_rn(c_hi[cqx + 1], wcx.y));
-                        top.y = __dadd_rn(__dmul_rn(c_hi[cqy], wcy.x), __dmul_rn(c_hi[cqy + 1], wcy.y));
-                    }
+            // ---- level 0 of the 1 node: U_f + P(U_c)   (MG_solver_CPU.cpp:700 + :569)
+            if (IN == IN_PROLONG) {
+                const int rq = rq_next;                           // row_cell[r], fetched one step ahead
+                const double2 wr = wr_next;
+                if (FAST || r + 1 <= N - 1) {
+                    rq_next = p.row_cell[r + 1];
+                    wr_next = p.row_w[r + 1];
+                }
+                if ((FAST || r <= N - 1) && rq != prev_rq) {      // the cell moved up one coarse row
+                    __syncwarp();                                 // the staged row was copied by all lanes
+                    const unsigned cs = warp_ring + slot_off + 1024;
+                    bot = top;
+                    top.x = __dadd_rn(__dmul_rn(lds1(cs + ox), wcx.x), __dmul_rn(lds1(cs + ox + 8), wcx.y));
+                    top.y = __dadd_rn(__dmul_rn(lds1(cs + oy), wcy.x), __dmul_rn(lds1(cs + oy + 8), wcy.y));
                     prev_rq = rq;
                 }
                 const double vx = __dadd_rn(__dmul_rn(bot.x, wr.x), __dmul_rn(top.x, wr.y));
                 const double vy = __dadd_rn(__dmul_rn(bot.y, wr.x), __dmul_rn(top.y, wr.y));
-                x.x = __dadd_rn(x.x, div_by_invariant(div_by_invariant(vx, p.c_dx, p.inv_c_dx), p.c_dx, p.inv_c_dx));
-                x.y = __dadd_rn(x.y, div_by_invariant(div_by_invariant(vy, p.c_dx, p.inv_c_dx), p.c_dx, p.inv_c_dx));
+                const double d = p.c_dx, y = p.inv_c_dx;
+                const double qx = div_fast(vx, d, y), qy = div_fast(vy, d, y);
+                double px = div_fast(qx, d, y), py = div_fast(qy, d, y);
+                const bool bad = div_unsafe(vx) | div_unsafe(qx) | div_unsafe(vy) | div_unsafe(qy);
+                if (__any_sync(0xffffffffu, bad)) {               // rare: redo with IEEE divisions
+                    px = __ddiv_rn(__ddiv_rn(vx, d), d);
+                    py = __ddiv_rn(__ddiv_rn(vy, d), d);
+                }
+                x.x = __dadd_rn(x.x, px);
+                x.y = __dadd_rn(x.y, py);
+                __syncwarp();                                     // every lane is done with the staged row
             }
+
+            // refill the slot with row r + DEPTH (the values above are in registers by now)
+            if (FAST) {
+                if (IN != IN_ZERO) cp_async16(ring_base + slot_off, Up + (ptrdiff_t)(r + STREAM_DEPTH) * ldn + cx);
+                if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
+                if (IN == IN_PROLONG) {
+                    const int c0 = cbase + 2 * lane;
+                    const double *src = p.Uc + (size_t)(rq_ahead + 1) * p.Nc + c0;
+                    const bool ok0 = c0 < p.Nc, ok1 = c0 + 1 < p.Nc;
+                    cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.Uc, ok0);
+                    cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.Uc, ok1);
+                    rq_ahead = p.row_cell[r + STREAM_DEPTH + 1];
+                }
+                cp_async_commit();
+            } else {
+                issue(r + STREAM_DEPTH, slot_off, rq_ahead);
+                if (IN == IN_PROLONG && r + STREAM_DEPTH + 1 <= N - 1) rq_ahead = p.row_cell[r + STREAM_DEPTH + 1];
+            }
+            slot_off += SLOT_BYTES;
+            if (slot_off == STREAM_DEPTH * SLOT_BYTES) slot_off = 0;
 
             if (NF > 0) fr[k % NR] = f_new;
 
@@ -307,21 +398,17 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
                 if (RES) {
                     const double2 d_cur = make_double2(-res.x, -res.y);   // D = -D (:277-280)
                     const int f_row = rho - 1;                            // lower fine row of the pair (f_row, rho)
-                    if (f_row >= own_r_lo && f_row < own_r_hi) {
-                        const int crow = p.f2c[f_row];
-                        if (crow >= 0) {
-                            const double cw = p.rw[crow];
-                            const double np = shfl_dn1(d_prev.x), nc = shfl_dn1(d_cur.x);
-                            const bool row_edge = crow == 0 || crow == p.M - 1;
-                            if (ccx >= 0) {
-                                const bool edge = row_edge || ccx == 0 || ccx == p.M - 1;
-                                p.Fc[(size_t)crow * p.M + ccx] = edge ? 0.0 : restrict_at(d_prev.x, d_prev.y, d_cur.x, d_cur.y, ax, cw);
-                            }
-                            if (ccy >= 0) {
-                                const bool edge = row_edge || ccy == 0 || ccy == p.M - 1;
-                                p.Fc[(size_t)crow * p.M + ccy] = edge ? 0.0 : restrict_at(d_prev.y, np, d_cur.y, nc, ay, cw);
-                            }
-                        }
+                    const double2 ri = rinfo_next;                        // {coarse row of f_row or -1, its weight}
+                    if (FAST || (f_row + 1 >= 0 && f_row + 1 <= N - 1)) rinfo_next = p.rrow[f_row + 1];
+                    else rinfo_next = make_double2(-1.0, 0.0);
+                    const int crow = (int)ri.x;
+                    if (crow >= 0 && f_row >= own_r_lo && f_row < own_r_hi) {
+                        const double cw = ri.y;
+                        const double np = shfl_dn1(d_prev.x), nc = shfl_dn1(d_cur.x);
+                        const bool row_edge = crow == 0 || crow == p.M - 1;
+                        double *out = p.Fc + (size_t)crow * p.M;
+                        if (ccx >= 0) out[ccx] = (row_edge || zx) ? 0.0 : restrict_at(d_prev.x, d_prev.y, d_cur.x, d_cur.y, ax, cw);
+                        if (ccy >= 0) out[ccy] = (row_edge || zy) ? 0.0 : restrict_at(d_prev.y, np, d_cur.y, nc, ay, cw);
                     }
                     d_prev = d_cur;
                 }
@@ -330,7 +417,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     };
 
     for (int rb = r_first; rb <= r_last; rb += U) {
-        const bool fast = strip_fast && rb - NLV >= 1 && rb + U - 1 + STREAM_DEPTH <= N - 1;
+        const bool fast = strip_fast && rb - NLV >= 1 && rb + U + STREAM_DEPTH <= N - 1;
         if (fast) chunk(BoolTag<true>(), rb);
         else chunk(BoolTag<false>(), rb);
     }
