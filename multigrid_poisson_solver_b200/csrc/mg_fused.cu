@@ -70,23 +70,24 @@ void launch_stream(StreamParams &p)
     Context &c = ctx();
     const int N = p.N;
     p.n_strips = (N + G::W - 1) / G::W;
-    p.n_sgroups = (p.n_strips + STREAM_WARPS - 1) / STREAM_WARPS;
-    // rows per task: enough CTAs to fill the chip twice, at most 256 rows (halo rows cost (2S+3)/H)
+    // Rows per task: about four tasks per resident warp when the grid is large enough (halo rows
+    // cost (2S+3)/H of extra work, so at least 32 rows), otherwise as many tasks as 16-row
+    // segments allow.
+    const int resident_warps = 2 * c.sm_count * STREAM_WARPS;
     int H = g_force_H;
     if (H <= 0) {
-        const int target_blocks = 2 * c.sm_count;
-        int n_segs = std::max(1, target_blocks / p.n_sgroups);
-        n_segs = std::min(n_segs, (N + 15) / 16);
-        H = (N + n_segs - 1) / n_segs;
+        const long long row_strips = (long long)N * p.n_strips;
+        H = (int)(row_strips / (4LL * resident_warps));
+        H = std::max(32, std::min(256, H));
+        if ((long long)((N + H - 1) / H) * p.n_strips < resident_warps) H = std::max(16, (int)(row_strips / resident_warps));
         H = std::min(256, (H + 7) / 8 * 8);
     }
     p.H = H;
     p.n_segs = (N + H - 1) / H;
-    const unsigned blocks = (unsigned)p.n_sgroups * (unsigned)p.n_segs;
-    if (ERR) {
-        p.partials = partials_buf(blocks);
-        p.counter = c.counters;
-    }
+    p.n_tasks = p.n_strips * p.n_segs;
+    const int blocks = std::max(1, std::min(2 * c.sm_count, (p.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS));
+    if (ERR) p.partials = partials_buf((size_t)p.n_tasks);
+    p.counter = c.counters + 8;   // [8] queue head, [9] finished warps (self-resetting)
     static bool opted_in = false;   // one flag per instantiation
     if (!opted_in) {
         check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem_bytes(IN)),

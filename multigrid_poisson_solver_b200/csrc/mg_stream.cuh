@@ -41,19 +41,22 @@ constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
 constexpr int STREAM_DEPTH = 8;         // rows in flight per warp (cp.async ring in shared memory), power of two
 // shared memory: [warp][slot][U | F (| coarse row, 1 node only)][lane] x 16 B
 __host__ __device__ constexpr int stream_slot_bytes(int in) { return (in == 2 ? 3 : 2) * 32 * 16; }
-__host__ __device__ constexpr int stream_smem_bytes(int in) { return STREAM_WARPS * STREAM_DEPTH * stream_slot_bytes(in); }
+__host__ __device__ constexpr int stream_smem_bytes(int in)
+{
+    return STREAM_WARPS * (STREAM_DEPTH * stream_slot_bytes(in) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
+}
 
 struct StreamParams {
     int N;                  // grid size (even)
     int H;                  // rows owned by one task
-    int n_strips, n_sgroups, n_segs;
+    int n_strips, n_segs, n_tasks;   // tasks (strip, row segment) are handed to warps through an atomic queue
     double h2, inv_h2;
     const double *Uin;      // IN_LOAD: U ; IN_PROLONG: U_f
     const double *F;
     double *Uout;
     // ERR
-    double *partials;
-    unsigned int *counter;
+    double *partials;       // [n_tasks] per-task error partials (fixed order => deterministic sum)
+    unsigned int *counter;  // [0] task queue head, [1] warps finished; both return to 0 at kernel end
     double *err_dev, *err_slot;
     // RES (restriction of the negated residual)
     int M;
@@ -151,6 +154,10 @@ __device__ __forceinline__ double2 lds2(unsigned smem_addr)
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts2(unsigned smem_addr, double2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(smem_addr), "d"(v.x), "d"(v.y) : "memory");
+}
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
@@ -169,9 +176,32 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N;
-    const int seg = blockIdx.x / p.n_sgroups;
-    const int strip = (blockIdx.x % p.n_sgroups) * STREAM_WARPS + warp;
-    const bool active = strip < p.n_strips;
+    const double h2 = p.h2, inv_h2 = p.inv_h2;
+    const double *__restrict__ Fp = p.F;
+    const double *__restrict__ Up = p.Uin;
+    double *__restrict__ Op = p.Uout;
+    const ptrdiff_t ldn = N;
+
+    // Streamed rows are staged through a per-warp ring in shared memory filled by cp.async:
+    // STREAM_DEPTH rows of U and F in flight per warp at no register cost.  Each lane copies
+    // and later reads back only its own 16 bytes, so no barrier is involved, only wait_group.
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    constexpr int SLOT_BYTES = stream_slot_bytes(IN);   // [U | F | coarse row][lane] x 16 B
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(stream_smem);
+    const unsigned warp_ring = smem0 + warp * (STREAM_DEPTH * SLOT_BYTES);
+    const unsigned ring_base = warp_ring + lane * 16;
+    const unsigned wc_addr = smem0 + STREAM_WARPS * (STREAM_DEPTH * SLOT_BYTES) + warp * 1024 + lane * 32;   // IN_PROLONG only
+
+  // Persistent warps: every warp pulls (strip, row segment) tasks from an atomic queue until it is
+  // empty, so there is no wave quantisation and no CTA waits for its slowest warp.
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = (int)atomicAdd(p.counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= p.n_tasks) break;
+    const int seg = task / p.n_strips;
+    const int strip = task - seg * p.n_strips;            // consecutive tasks = adjacent strips of one row segment
+    constexpr bool active = true;
 
     const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
     const int c_first = own_c_lo - G::HL;                       // first column of the 64-wide window (even)
@@ -182,13 +212,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     const bool strip_fast = c_first >= 1 && c_first + 63 <= N - 2;   // every column of the window is interior
     const int own_r_lo = seg * p.H, own_r_hi = min(own_r_lo + p.H, N);
     const int r_first = max(0, own_r_lo - G::ROW_LEAD);
-    const int r_last = active ? min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD) : -1;   // idle warps skip the loop
-
-    const double h2 = p.h2, inv_h2 = p.inv_h2;
-    const double *__restrict__ Fp = p.F;
-    const double *__restrict__ Up = p.Uin;
-    double *__restrict__ Op = p.Uout;
-    const ptrdiff_t ldn = N;
+    const int r_last = min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD);
 
     // Register state.  Every index below is a compile-time constant after unrolling, so the
     // arrays live in registers and rotate by renaming, not by moves.
@@ -199,13 +223,6 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
 #pragma unroll
     for (int t = 0; t < NR; ++t) fr[t] = make_double2(0.0, 0.0);
 
-    // Streamed rows are staged through a per-warp ring in shared memory filled by cp.async:
-    // STREAM_DEPTH rows of U and F in flight per warp at no register cost.  Each lane copies
-    // and later reads back only its own 16 bytes, so no barrier is involved, only wait_group.
-    extern __shared__ __align__(16) unsigned char stream_smem[];
-    constexpr int SLOT_BYTES = stream_slot_bytes(IN);   // [U | F | coarse row][lane] x 16 B
-    const unsigned warp_ring = (unsigned)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_DEPTH * SLOT_BYTES);
-    const unsigned ring_base = warp_ring + lane * 16;
     unsigned slot_off = 0;                       // byte offset of the slot that holds the row of the current step
 
     // ---- restriction state
@@ -231,14 +248,17 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     // holds doubles [cbase, cbase+64) of coarse row row_cell[r]+1 (the upper row of its cell).
     int cqx = 0, cqy = 0, prev_rq = -4, cbase = 0, rq_next = 0, rq_ahead = 0;
     unsigned ox = 0, oy = 0;                     // byte offsets of this lane's two cells inside a staged coarse row
-    double2 wcx = make_double2(0.0, 0.0), wcy = wcx, bot = wcx, top = wcx, wr_next = wcx;
+    double2 bot = make_double2(0.0, 0.0), top = bot, wr_next = bot;
     if (IN == IN_PROLONG) {
+        double2 wcx = bot, wcy = bot;
         if (col_ok) {
             cqx = p.col_cell[cx];
             cqy = p.col_cell[cx + 1];
             wcx = p.col_w[cx];
             wcy = p.col_w[cx + 1];
         }
+        sts2(wc_addr, wcx);                       // this lane's column weights live in shared memory (register relief)
+        sts2(wc_addr + 16, wcy);
         cbase = __reduce_min_sync(0xffffffffu, col_ok ? cqx : 0x7fffffff) & ~1;
         ox = col_ok ? (unsigned)(cqx - cbase) * 8u : 0u;     // lanes outside the grid read slot element 0 (unused)
         oy = col_ok ? (unsigned)(cqy - cbase) * 8u : 0u;
@@ -279,6 +299,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
         // lower coarse row of the first cell: the only one that is not staged
         const double *c_lo = p.Uc + (size_t)rq_next * p.Nc;
         if (col_ok) {
+            const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
             top.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
             top.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
         }
@@ -310,6 +331,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
                     __syncwarp();                                 // the staged row was copied by all lanes
                     const unsigned cs = warp_ring + slot_off + 1024;
                     bot = top;
+                    const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
                     top.x = __dadd_rn(__dmul_rn(lds1(cs + ox), wcx.x), __dmul_rn(lds1(cs + ox + 8), wcx.y));
                     top.y = __dadd_rn(__dmul_rn(lds1(cs + oy), wcy.x), __dmul_rn(lds1(cs + oy + 8), wcy.y));
                     prev_rq = rq;
@@ -423,29 +445,40 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     }
 
     cp_async_wait<0>();
+    __syncwarp();                                 // the ring is reused by the next task
     if (ERR) {
-        __shared__ double red_smem[32];
-        __shared__ bool is_last;
-        const double total = block_sum<STREAM_WARPS * 32>(err_acc, red_smem);
-        if (threadIdx.x == 0) {
-            p.partials[blockIdx.x] = total;
-            __threadfence();
-            is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (!is_last) return;
+        double v = err_acc;                       // fixed shuffle tree => the task's partial is deterministic
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
+        if (lane == 0) p.partials[task] = v;
+    }
+  }  // task loop
+
+    // ---- the last warp to finish resets the queue and folds the per-task partials in task order
+    unsigned int done = 0;
+    if (lane == 0) {
         __threadfence();
+        done = atomicAdd(p.counter + 1, 1u);
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != gridDim.x * STREAM_WARPS - 1) return;
+    __threadfence();
+    if (ERR) {
         double s = 0.0;
-        for (unsigned k = threadIdx.x; k < gridDim.x; k += STREAM_WARPS * 32) s = __dadd_rn(s, __ldcg(&p.partials[k]));
-        s = block_sum<STREAM_WARPS * 32>(s, red_smem);
-        if (threadIdx.x == 0) {
+        for (int k = lane; k < p.n_tasks; k += 32) s = __dadd_rn(s, __ldcg(&p.partials[k]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+        if (lane == 0) {
             double e = __dadd_rn(s, s);                           // sum1 + sum2 over the same parity (:621)
             e = __ddiv_rn(e, (double)N);
             e = __ddiv_rn(e, (double)N);
             if (p.err_dev) *p.err_dev = e;
             if (p.err_slot) { *p.err_slot = e; __threadfence_system(); }
-            *p.counter = 0u;
         }
+    }
+    if (lane == 0) {
+        p.counter[0] = 0u;
+        p.counter[1] = 0u;
     }
 }
 
