@@ -60,7 +60,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -305,29 +305,62 @@ def main():
 
 
 def dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, unfused):
-    """Times the kernel that dominates the V-cycle (the fine-grid smoothing pass) alone, with
-    CUDA events on the stream it is launched on; inputs (2 GiB grids) exceed L2."""
-    n = N * N
-    U, W, F = mg.DeviceGrid(N), mg.DeviceGrid(N), mg.DeviceGrid(N)
+    """Times the kernels that make up the fine level of the V-cycle alone, with CUDA events on the
+    stream they are launched on (inputs are 2 GiB grids, far larger than L2), and reports the one
+    that takes the largest share of the cycle (profiles/*launches*.csv: the fused 1 node).
+    `achieved` uses the compulsory bytes of SURVEY.md 8(d): every distinct array once."""
+    n, M = N * N, N // 2
+    m = M * M
+    U, W, F, Fc, Uc = mg.DeviceGrid(N), mg.DeviceGrid(N), mg.DeviceGrid(N), mg.DeviceGrid(M), mg.DeviceGrid(M)
     lib.getSource(N, 1.0, F.ptr, 0.0, 0.0)
+    lib.getSource(M, 1.0, Uc.ptr, 0.0, 0.0)
     lib.mgGridZero(N, U.ptr)
+    slot = lib.mgScalarSlot(100)
     reps = 10
-    out = {}
-    # (a) one Jacobi sweep, out of place: reads U, F, writes U' = 24 B per point
-    for _ in range(3):
-        lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 1, W.ptr, None)
-    lib.mgSync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(reps):
-        lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 1, W.ptr, None)
-    e1.record(stream)
-    lib.mgSync()
-    ms = e0.elapsed_time(e1) / reps
-    out = {"bound": "hbm", "kernel": "k_sweep (one Jacobi sweep, fine grid N=%d)" % N, "achieved": 24.0 * n / (ms * 1e6),
-           "peak": hbm_peak, "unit": "GB/s", "frac": 24.0 * n / (ms * 1e6) / hbm_peak, "traffic": None,
-           "algorithmic_bytes_per_launch": 24.0 * n, "ms_per_launch": ms, "peak_source": peak_src}
-    return out
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        lib.mgSync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        lib.mgSync()
+        return e0.elapsed_time(e1) / reps
+
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = {k.split()[0]: v["traffic"] for k, v in json.load(f).items()}
+
+    def entry(name, kernel, ms, nbytes, what):
+        return {"name": name, "kernel": kernel, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
+                "achieved": nbytes / (ms * 1e6), "frac": nbytes / (ms * 1e6) / hbm_peak, "bytes_are": what,
+                "traffic": traffic.get(name)}
+
+    kernels = []
+    if unfused:
+        ms = timeit(lambda: lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 1, W.ptr, None))
+        kernels.append(entry("sweep", "k_stream<1,IN_LOAD> (one Jacobi sweep)", ms, 24.0 * n, "U in, F in, U out"))
+    else:
+        ms = timeit(lambda: lib.mgUpLeg(M, Uc.ptr, N, 1.0, U.ptr, W.ptr, F.ptr, 3, slot))
+        kernels.append(entry("up_leg", "k_stream<3,IN_PROLONG,ERR> (1 node: prolong+add+3 sweeps+error)", ms, 24.0 * n + 8.0 * m,
+                             "U_f in, F in, U_f out, U_c in (unfused sequence moves 122 B/point)"))
+        ms = timeit(lambda: lib.mgDownLeg(N, 1.0, U.ptr, W.ptr, F.ptr, 3, 1, M, Fc.ptr, slot))
+        kernels.append(entry("down_leg", "k_stream<3,IN_ZERO,ERR,RES> (-1 node: 3 sweeps+error+residual+negate+restrict)", ms,
+                             16.0 * n + 8.0 * m, "F in, U out, F_c out (unfused sequence moves 146 B/point)"))
+        ms = timeit(lambda: lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 3, W.ptr, slot))
+        kernels.append(entry("smooth_S3", "k_stream<3,IN_LOAD,ERR> (doSmoothing step=3: 3 sweeps+error)", ms, 24.0 * n,
+                             "U in, F in, U out (unfused sequence moves 88 B/point)"))
+    top = kernels[0]
+    return {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": top["frac"], "traffic": top["traffic"], "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
+            "ms_per_launch": top["ms_per_launch"], "peak_source": peak_src, "grid": "N=%d fine level" % N,
+            "traffic_source": "profiles/r01_kernel_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
+            "kernels": kernels}
 
 
 if __name__ == "__main__":

@@ -40,7 +40,8 @@ constexpr int STREAM_WARPS = 8;         // warps (= strips) per CTA
 constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
 constexpr int STREAM_DEPTH = 8;         // rows in flight per warp (cp.async ring in shared memory), power of two
 // shared memory: [warp][slot][U | F (| coarse row, 1 node only)][lane] x 16 B
-__host__ __device__ constexpr int stream_slot_bytes(int in) { return (in == 2 ? 3 : 2) * 32 * 16; }
+// the 1 node adds the staged coarse row (512 B) and the row's {row_w, row_cell} entry (32 B)
+__host__ __device__ constexpr int stream_slot_bytes(int in) { return in == 2 ? 3 * 512 + 32 : 2 * 512; }
 __host__ __device__ constexpr int stream_smem_bytes(int in)
 {
     return STREAM_WARPS * (STREAM_DEPTH * stream_slot_bytes(in) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
@@ -138,6 +139,17 @@ __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void *gsrc, 
 {
     const int src_bytes = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void *gsrc, bool valid)
+{
+    const int src_bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ int lds_int(unsigned smem_addr)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ double lds1(unsigned smem_addr)
 {
@@ -246,9 +258,12 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     // ---- prolongation state
     // Coarse rows are staged through the third part of each ring slot: the slot of fine row r
     // holds doubles [cbase, cbase+64) of coarse row row_cell[r]+1 (the upper row of its cell).
-    int cqx = 0, cqy = 0, prev_rq = -4, cbase = 0, rq_next = 0, rq_ahead = 0;
+    // row_cell[] / row_w[] of fine row r travel in the ring slot of row r; the coarse row index needed
+    // when a copy is ISSUED (DEPTH rows ahead) comes from a lane-distributed table: lane l holds
+    // row_cell[tab_base + l], looked up by shuffle and refilled every 32 rows (double buffered).
+    int cqx = 0, cqy = 0, prev_rq = -4, cbase = 0, tab = 0, tab_nxt = 0, tab_base = 0;
     unsigned ox = 0, oy = 0;                     // byte offsets of this lane's two cells inside a staged coarse row
-    double2 bot = make_double2(0.0, 0.0), top = bot, wr_next = bot;
+    double2 bot = make_double2(0.0, 0.0), top = bot;
     if (IN == IN_PROLONG) {
         double2 wcx = bot, wcy = bot;
         if (col_ok) {
@@ -259,12 +274,23 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
         }
         sts2(wc_addr, wcx);                       // this lane's column weights live in shared memory (register relief)
         sts2(wc_addr + 16, wcy);
+        tab_base = r_first;
+        tab = p.row_cell[min(r_first + lane, N - 1)];
+        tab_nxt = p.row_cell[min(r_first + 32 + lane, N - 1)];
         cbase = __reduce_min_sync(0xffffffffu, col_ok ? cqx : 0x7fffffff) & ~1;
         ox = col_ok ? (unsigned)(cqx - cbase) * 8u : 0u;     // lanes outside the grid read slot element 0 (unused)
         oy = col_ok ? (unsigned)(cqy - cbase) * 8u : 0u;
     }
     double err_acc = 0.0;
 
+    auto cell_of_row = [&](int r) {              // row_cell[min(r, N-1)] for the row being issued (non-decreasing r)
+        if (r - tab_base >= 32) {
+            tab = tab_nxt;
+            tab_base += 32;
+            tab_nxt = p.row_cell[min(tab_base + 32 + lane, N - 1)];
+        }
+        return __shfl_sync(0xffffffffu, tab, r - tab_base);
+    };
     // guarded issue of level-0 row r and of F row r-1 (first used at step r) into ring slot `off`;
     // for the 1 node also the upper coarse row of fine row r's cell (`rq` = row_cell[r])
     auto issue = [&](int r, unsigned off, int rq) {
@@ -283,27 +309,30 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
             const bool ok0 = row_ok && c0 < p.Nc, ok1 = row_ok && c0 + 1 < p.Nc;
             cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.Uc, ok0);
             cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.Uc, ok1);
+            if (lane == 0) {
+                const int rr = row_ok ? r : 0;
+                cp_async16(warp_ring + off + 1536, p.row_w + rr, row_ok);
+                cp_async4(warp_ring + off + 1552, p.row_cell + rr, row_ok);
+            }
         }
         cp_async_commit();
     };
 #pragma unroll
     for (int d = 0; d < STREAM_DEPTH; ++d) {
         int rq = 0;
-        if (IN == IN_PROLONG && active && r_first + d <= N - 1) rq = p.row_cell[r_first + d];
+        if (IN == IN_PROLONG) rq = cell_of_row(r_first + d);
         issue(r_first + d, d * SLOT_BYTES, rq);
     }
     if (IN == IN_PROLONG && active) {
-        rq_next = p.row_cell[r_first];
-        wr_next = p.row_w[r_first];
-        if (r_first + STREAM_DEPTH <= N - 1) rq_ahead = p.row_cell[r_first + STREAM_DEPTH];
+        const int rq_first = __shfl_sync(0xffffffffu, tab, 0);
         // lower coarse row of the first cell: the only one that is not staged
-        const double *c_lo = p.Uc + (size_t)rq_next * p.Nc;
+        const double *c_lo = p.Uc + (size_t)rq_first * p.Nc;
         if (col_ok) {
             const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
             top.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
             top.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
         }
-        prev_rq = rq_next - 1;                    // so that the first step shifts `top` down and loads the upper row
+        prev_rq = rq_first - 1;                   // so that the first step shifts `top` down and loads the upper row
     }
 
     // One chunk = U consecutive steps.  FAST: every row touched by every stage is an interior
@@ -321,14 +350,10 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
 
             // ---- level 0 of the 1 node: U_f + P(U_c)   (MG_solver_CPU.cpp:700 + :569)
             if (IN == IN_PROLONG) {
-                const int rq = rq_next;                           // row_cell[r], fetched one step ahead
-                const double2 wr = wr_next;
-                if (FAST || r + 1 <= N - 1) {
-                    rq_next = p.row_cell[r + 1];
-                    wr_next = p.row_w[r + 1];
-                }
+                __syncwarp();                                     // the slot was filled by all lanes (and lane 0's table entry)
+                const double2 wr = lds2(warp_ring + slot_off + 1536);   // row_w[r]
+                const int rq = lds_int(warp_ring + slot_off + 1552);    // row_cell[r]
                 if ((FAST || r <= N - 1) && rq != prev_rq) {      // the cell moved up one coarse row
-                    __syncwarp();                                 // the staged row was copied by all lanes
                     const unsigned cs = warp_ring + slot_off + 1024;
                     bot = top;
                     const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
@@ -357,16 +382,18 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
                 if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
                 if (IN == IN_PROLONG) {
                     const int c0 = cbase + 2 * lane;
-                    const double *src = p.Uc + (size_t)(rq_ahead + 1) * p.Nc + c0;
+                    const double *src = p.Uc + (size_t)(cell_of_row(r + STREAM_DEPTH) + 1) * p.Nc + c0;
                     const bool ok0 = c0 < p.Nc, ok1 = c0 + 1 < p.Nc;
                     cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.Uc, ok0);
                     cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.Uc, ok1);
-                    rq_ahead = p.row_cell[r + STREAM_DEPTH + 1];
+                    if (lane == 0) {
+                        cp_async16(warp_ring + slot_off + 1536, p.row_w + r + STREAM_DEPTH, true);
+                        cp_async4(warp_ring + slot_off + 1552, p.row_cell + r + STREAM_DEPTH, true);
+                    }
                 }
                 cp_async_commit();
             } else {
-                issue(r + STREAM_DEPTH, slot_off, rq_ahead);
-                if (IN == IN_PROLONG && r + STREAM_DEPTH + 1 <= N - 1) rq_ahead = p.row_cell[r + STREAM_DEPTH + 1];
+                issue(r + STREAM_DEPTH, slot_off, IN == IN_PROLONG ? cell_of_row(r + STREAM_DEPTH) : 0);
             }
             slot_off += SLOT_BYTES;
             if (slot_off == STREAM_DEPTH * SLOT_BYTES) slot_off = 0;
