@@ -196,6 +196,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    hbm_peak, peak_src = peaks()
+    if world > 1:
+        return multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, local, barrier, max_over_ranks,
+                             hbm_peak, peak_src)
+
     N = args.nmax
     n = N * N
     path = write_cycle(cycles.v_cycle(N, 8))
@@ -267,7 +272,6 @@ def main():
         del hF, hU
 
     # ---- roofline of the dominant kernel, timed alone on the library's stream -----------------
-    hbm_peak, peak_src = peaks()
     roof = dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, args.unfused)
 
     line = {
@@ -301,6 +305,111 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+WEAK_N = {1: 16384, 2: 23168, 4: 32768, 8: 46336}   # N^2 per GPU constant (16384^2), even ladders down to the threshold
+
+
+def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, local, barrier, max_over_ranks, hbm_peak, peak_src):
+    """Weak scaling of the row-slab driver: the grid grows with the GPU count so that every GPU keeps
+    16384^2 fine points; one process per GPU, NCCL halo exchange, levels < 2048 rows on rank 0."""
+    threshold = 2048
+    N = WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256) if args.nmax == 16384 else args.nmax
+    n = N * N
+    base_n = 16384 * 16384
+
+    def bcast(b):
+        obj = [b]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+
+    mg.dist_init(rank, world, bcast)
+    path = write_cycle(cycles.v_cycle(N, 8))
+    flags = mg.RUN_FUSED | mg.RUN_QUIET | mg.RUN_NO_FINAL_ERROR | mg.RUN_SKIP_SOURCE
+    recs = (api.TraceRec * 64)()
+    res = api.CycleResult()
+    import ctypes as C
+    lo, hi = C.c_int(0), C.c_int(0)
+
+    def one_cycle(u_host=None):
+        rc = lib.mgDistRunCycleFile(os.fsencode(path), threshold, flags, u_host, C.byref(lo), C.byref(hi), recs, 64, res)
+        if rc != 0:
+            raise SystemExit("mgDistRunCycleFile failed: %d %s" % (rc, lib.mgLastError().decode()))
+        return res.launches
+
+    for _ in range(max(args.warmup, 1)):
+        one_cycle()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            launches += one_cycle()
+        ev1.record(stream)
+        barrier()
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = clk.summary()
+    ms_per_step = total_ms / args.steps
+    value = (n / base_n) * 1000.0 / ms_per_step          # V-cycles/s in units of 16384^2 fine points
+    trace = [dict(node=r.node, N=r.N, steps=r.steps, err=r.err) for r in recs[:res.n_recs]]
+
+    # correctness of the distributed result: final error against the analytic solution
+    chk = mg.run_cycle_dist(path, threshold, mg.RUN_FUSED | mg.RUN_QUIET | mg.RUN_SKIP_SOURCE)
+    mg_error = chk["mg_error"]
+
+    # ---- end to end: every rank uploads its source slab from pinned memory and reads its rows back
+    e2e = None
+    if not args.no_e2e:
+        r0, rows, olo, ohi = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        lib.mgDistSourceSlab(N, threshold, C.byref(r0), C.byref(rows), C.byref(olo), C.byref(ohi))
+        hF = torch.empty(max(rows.value, 1) * N, dtype=torch.float64).pin_memory()
+        hU = torch.empty(max(ohi.value - olo.value, 1) * N, dtype=torch.float64).pin_memory()
+        lib.mgDistDownloadSource(N, hF.data_ptr())
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def one_e2e():
+            lib.mgDistUploadSource(N, threshold, hF.data_ptr())
+            one_cycle(hU.data_ptr())
+
+        one_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            one_e2e()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1000.0 * wall)) / e2e_steps
+        e2e = {"value": (n / base_n) * 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * rows.value * N,
+               "d2h_bytes_per_step": 8 * (ohi.value - olo.value) * N, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "call": "per rank: mgDistUploadSource(pinned slab) + mgDistRunCycleFile(U rows -> pinned host); bytes are per rank"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "Vcycle.txt shape (con_step=3, con_N=1, GS 1e-7 opt 1) at N_max=%d N_min=8: one grid row-slab "
+                               "partitioned over %d GPUs, 16384^2 fine points per GPU" % (N, world),
+                   "value_is": "V-cycles/s x (N_max/16384)^2, i.e. in units of the 1-GPU workload",
+                   "driver": "mgDistRunCycleFile: fused nodes on row slabs, NCCL send/recv halo exchange (%d rows), "
+                             "levels < %d rows agglomerated on rank 0" % (8, threshold),
+                   "l2": "inputs exceed L2", "parallelism": "row slabs x%d" % world},
+        "fine_dof_cycles_per_s": n * 1000.0 / ms_per_step, "global_ms_per_cycle": ms_per_step, "mg_error": mg_error,
+        "trace_errors": [t["err"] for t in trace if t["node"] != 0], "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "whole V-cycle on slabs (fused nodes)", "achieved": 44.0 * n * 4 / 3 / (ms_per_step * 1e6) / world,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": 44.0 * n * 4 / 3 / (ms_per_step * 1e6) / world / hbm_peak, "traffic": None,
+                     "note": "per GPU: compulsory bytes of the fused cycle (44 B per fine point per level, ladder sum 4/3) / time; "
+                             "per-kernel rooflines are reported by the 1-GPU run", "peak_source": peak_src},
+    }
+    os.unlink(path)
+    if rank == 0:
+        print(json.dumps(line))
+    lib.mgDistShutdown()
+    dist.destroy_process_group()
     return 0
 
 

@@ -139,6 +139,32 @@ int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_t
 int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double *U_host,
                        mgTraceRec *recs, int max_recs, mgCycleResult *res);
 
+/* ------------------------------------------------------------ multi-GPU (row slabs)
+ * One process per GPU.  Levels with at least `threshold` rows are partitioned into row slabs
+ * (one per rank) with halo exchange per fused pass; smaller levels are agglomerated on rank 0.
+ * Rendezvous: rank 0 calls mgDistUniqueId, the host program broadcasts the 128 bytes (e.g. with
+ * torch.distributed), every rank calls mgDistInit.  NCCL is bound with dlopen at run time. */
+int mgDistUniqueId(void *out128);
+int mgDistInit(int rank, int world, const void *id128);
+void mgDistShutdown(void);
+/* Runs a cycle file on all ranks collectively (fused driver, MG_RUN_QUIET / MG_RUN_NO_FINAL_ERROR
+ * honoured).  U_own_host, if non-NULL, receives this rank's owned rows [*own_lo, *own_hi) of the
+ * final solution (host buffer of at least N_max*N_max doubles is always enough). */
+int mgDistRunCycleFile(const char *path, int threshold, int flags, double *U_own_host, int *own_lo, int *own_hi,
+                       mgTraceRec *recs, int max_recs, mgCycleResult *res);
+/* Host-buffer path of the slab driver: geometry of this rank's top-level slab (rows
+ * [row0, row0+rows) held incl. halo, [own_lo, own_hi) owned), upload of its source rows from a
+ * host buffer (used by the next mgDistRunCycleFile calls that pass MG_RUN_SKIP_SOURCE), and
+ * download of the cached source slab. */
+int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, int *own_hi);
+int mgDistUploadSource(int N, int threshold, const double *F_slab_host);
+int mgDistDownloadSource(int N, double *F_slab_host);
+/* The same slab algorithm with all `world` ranks emulated inside this process on the current GPU
+ * (device-to-device copies instead of NCCL): lets the slab logic be verified on one GPU.
+ * U_host (N_max^2) receives the assembled solution. */
+int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags, double *U_host,
+                          mgTraceRec *recs, int max_recs, mgCycleResult *res);
+
 /* CSV dump in the reference's format (doPrint2File, MG_solver_CPU.cpp:735-754) from a host array */
 int mgPrint2File(int N, const double *U_host, const char *file_name);
 

@@ -63,6 +63,16 @@ ABI = {
     "mgRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),
+    "mgDistUniqueId": (C.c_int, [_vp]),
+    "mgDistInit": (C.c_int, [C.c_int, C.c_int, _vp]),
+    "mgDistShutdown": (None, []),
+    "mgDistSourceSlab": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mgDistUploadSource": (C.c_int, [C.c_int, C.c_int, _vp]),
+    "mgDistDownloadSource": (C.c_int, [C.c_int, _vp]),
+    "mgDistRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
+    "mgDistEmuRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(TraceRec), C.c_int,
+                                        C.POINTER(CycleResult)]),
 }
 
 _lib = None
@@ -283,3 +293,56 @@ def run_cycle_host(path, flags=RUN_FUSED | RUN_QUIET, F_host=None, want_U=True, 
 def run_cycle(path, flags=RUN_FUSED | RUN_QUIET, max_recs=8192):
     """mgRunCycleFile with the source generated on the device; the solution stays on the device."""
     return _run("mgRunCycleFile", path, flags, None, 0, max_recs)
+
+
+def run_cycle_dist_emulated(path, world, threshold, flags=RUN_FUSED | RUN_QUIET, max_recs=8192):
+    """mgDistEmuRunCycleFile: the row-slab multi-GPU algorithm with all ranks emulated on this GPU."""
+    l = _need()
+    N = _n_max(path)
+    recs = (TraceRec * max_recs)()
+    res = CycleResult()
+    U = np.empty(N * N)
+    rc = l.mgDistEmuRunCycleFile(os.fsencode(path), world, threshold, flags, U.ctypes.data, recs, max_recs, C.byref(res))
+    if rc != 0:
+        msg = l.mgLastError().decode()
+        l.mgClearError()
+        raise MGLibraryError("mgDistEmuRunCycleFile(%s) failed with code %d %s" % (path, rc, msg))
+    trace = [dict(node=r.node, N=r.N, steps=r.steps, err=r.err) for r in recs[:res.n_recs]]
+    return dict(trace=trace, U=U, N=res.N, mg_error=res.mg_error, time_ms=res.time_ms, wall_ms=res.wall_ms,
+                launches=res.launches)
+
+
+def dist_init(rank, world, broadcast_bytes):
+    """NCCL rendezvous for the slab driver.  `broadcast_bytes(buf_or_None) -> bytes` must return
+    rank 0's 128-byte id on every rank (e.g. via torch.distributed.broadcast_object_list)."""
+    l = _need()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0 and l.mgDistUniqueId(buf) != 0:
+        _check()
+    data = broadcast_bytes(bytes(buf) if rank == 0 else None)
+    buf2 = (C.c_ubyte * 128).from_buffer_copy(data)
+    if l.mgDistInit(rank, world, buf2) != 0:
+        _check()
+        raise MGLibraryError("mgDistInit failed")
+
+
+def run_cycle_dist(path, threshold, flags=RUN_FUSED | RUN_QUIET, want_U=False, max_recs=8192):
+    """mgDistRunCycleFile (collective).  Returns this rank's owned rows when want_U."""
+    l = _need()
+    N = _n_max(path)
+    recs = (TraceRec * max_recs)()
+    res = CycleResult()
+    lo, hi = C.c_int(0), C.c_int(0)
+    U = np.empty(N * N) if want_U else None
+    rc = l.mgDistRunCycleFile(os.fsencode(path), threshold, flags, U.ctypes.data if want_U else None, C.byref(lo), C.byref(hi),
+                              recs, max_recs, C.byref(res))
+    if rc != 0:
+        msg = l.mgLastError().decode()
+        l.mgClearError()
+        raise MGLibraryError("mgDistRunCycleFile(%s) failed with code %d %s" % (path, rc, msg))
+    trace = [dict(node=r.node, N=r.N, steps=r.steps, err=r.err) for r in recs[:res.n_recs]]
+    out = dict(trace=trace, N=res.N, mg_error=res.mg_error, time_ms=res.time_ms, wall_ms=res.wall_ms, launches=res.launches,
+               own=(lo.value, hi.value))
+    if want_U:
+        out["U_own"] = U[: (hi.value - lo.value) * N].copy()
+    return out

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgb200.so")
 EXE = os.path.join(HERE, "MG_GPU")
-SOURCES = ["mg_abi.cu", "mg_kernels.cu", "mg_fused.cu", "mg_exact.cu", "mg_driver.cpp"]
+SOURCES = ["mg_abi.cu", "mg_kernels.cu", "mg_fused.cu", "mg_exact.cu", "mg_dist.cu", "mg_driver.cpp"]
 HEADERS = ["mg_context.h", "mg_kernels.h", "mg_fused.h", "mg_device.cuh", "mg_stream.cuh", os.path.join("..", "..", "include", "mg_abi.h")]
 
 NVCC_FLAGS = [
@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-fmad=false",            # bit parity with the -O0 CPU reference: never contract to FMA
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-Xptxas", "-v",
+    "-I/usr/include",         # nccl.h (types only; the library is bound with dlopen at run time)
 ]
 
 
@@ -38,7 +39,7 @@ def build(force=False, verbose=False):
     env.pop("CC", None)
     env.pop("CXX", None)
     if force or _newer(LIB, deps):
-        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-ccbin", "g++"]
+        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-ccbin", "g++", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -85,8 +85,36 @@ double *slot_device_ptr(double *host_slot)
 
 static size_t grid_bytes(int N)
 {
-    const size_t b = (size_t)N * (size_t)N * sizeof(double);
-    return (b + 255) / 256 * 256;
+    return (size_t)N * (size_t)N * sizeof(double);
+}
+
+void *pool_alloc(size_t bytes)
+{
+    Context &c = ctx();
+    bytes = (bytes + 255) / 256 * 256;
+    void *p = nullptr;
+    auto it = c.free_lists.find(bytes);
+    if (it != c.free_lists.end() && !it->second.empty()) {
+        p = it->second.back();
+        it->second.pop_back();
+        c.pooled_bytes -= bytes;
+    } else if (!check(cudaMalloc(&p, bytes), "cudaMalloc grid")) {
+        return nullptr;
+    }
+    c.live[p] = bytes;
+    return p;
+}
+
+void pool_free(void *ptr)
+{
+    if (!ptr) return;
+    Context &c = ctx();
+    auto it = c.live.find(ptr);
+    if (it == c.live.end()) { fail(-7, "pool_free: pointer was not allocated by the pool"); return; }
+    // stream-ordered reuse: every consumer is queued on the same stream, so the block can be handed out again at once
+    c.free_lists[it->second].push_back(ptr);
+    c.pooled_bytes += it->second;
+    c.live.erase(it);
 }
 
 }  // namespace mg
@@ -169,31 +197,13 @@ double *mgScalarSlot(int index)
 double *mgGridAlloc(int N)
 {
     if (!ensure_ready()) return nullptr;
-    Context &c = ctx();
-    const size_t bytes = grid_bytes(N);
-    void *p = nullptr;
-    auto it = c.free_lists.find(bytes);
-    if (it != c.free_lists.end() && !it->second.empty()) {
-        p = it->second.back();
-        it->second.pop_back();
-        c.pooled_bytes -= bytes;
-    } else if (!check(cudaMalloc(&p, bytes), "cudaMalloc grid")) {
-        return nullptr;
-    }
-    c.live[p] = bytes;
-    return (double *)p;
+    return (double *)pool_alloc(grid_bytes(N));
 }
 
 void mgGridFree(double *grid)
 {
     if (!grid || !ensure_ready()) return;
-    Context &c = ctx();
-    auto it = c.live.find(grid);
-    if (it == c.live.end()) { fail(-7, "mgGridFree: pointer was not allocated by mgGridAlloc"); return; }
-    // stream-ordered reuse: every consumer is queued on the same stream, so the block can be handed out again at once
-    c.free_lists[it->second].push_back(grid);
-    c.pooled_bytes += it->second;
-    c.live.erase(it);
+    pool_free(grid);
 }
 
 void mgGridZero(int N, double *grid)

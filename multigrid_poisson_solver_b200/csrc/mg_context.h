@@ -66,6 +66,8 @@ bool ensure_ready();
 void fail(int code, const std::string &msg);
 bool check(cudaError_t e, const char *what);
 
+void *pool_alloc(size_t bytes);   // size-keyed, stream-ordered pool behind mgGridAlloc
+void pool_free(void *ptr);
 double *scratch_grid(size_t elems);
 double *partials_buf(size_t elems);
 double *slot_device_ptr(double *host_slot);  // pinned host slot -> device alias, or nullptr

@@ -1,0 +1,830 @@
+// mg_dist.cu -- row-slab multi-GPU cycle driver.
+//
+// Fine levels are partitioned into contiguous row slabs, one per rank (one process per GPU);
+// every slab carries HALO extra rows on each side.  A fused pass needs the halo rows of its
+// input to be current, so the protocol per node is
+//     -1 node : [exchange U halos unless U = 0]  pass(es)  ->  F_c rows  ->  exchange F_c halos
+//      1 node : exchange U_f and U_c halos       pass(es)
+// with one exchange between two passes of the same node (step > 3).  The coarse partition is
+// INDUCED by the fine one through the reference's floor map (a rank owns the coarse rows whose
+// lower fine row it owns), so restriction needs no communication at all and prolongation only
+// the coarse halo.  Levels below `threshold` rows are agglomerated on rank 0 (gather of F_c on
+// the way down, scatter of U_c with halos on the way up); the other ranks idle there.
+// The smoothing error is the all-reduced sum of the slabs' red-parity sums.
+//
+// Two communicators implement the same three primitives (point-to-point row transfers, scalar
+// all-reduce):
+//   EmuComm   all ranks live in this process on the current GPU (device-to-device copies).  It
+//             exists so the whole slab logic is testable bit-for-bit on one GPU.
+//   NcclComm  one rank per process; ncclSend/ncclRecv groups and ncclAllReduce on the library's
+//             stream.  NCCL is bound at run time (dlopen of the libnccl.so.2 the host program --
+//             e.g. torch -- already loaded), so the library has no link-time NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mg_abi.h"
+#include "mg_fused.h"
+#include "mg_kernels.h"
+
+namespace mg {
+namespace {
+
+constexpr int HALO = 8;           // >= S+2 for S <= 3 sweeps per pass, on the fine and (ratio >= 1.2) the coarse side
+constexpr double TRIGGER = 0.01;  // MG_solver_CPU.cpp:99
+
+struct Xfer {                     // `count` doubles from src (valid on src_rank) to dst (valid on dst_rank)
+    int src_rank, dst_rank;
+    const double *src;
+    double *dst;
+    size_t count;
+};
+
+class Comm {
+public:
+    virtual ~Comm() {}
+    int world = 1;
+    std::vector<int> local;       // ranks living in this process
+    bool is_local(int r) const { return std::find(local.begin(), local.end(), r) != local.end(); }
+    virtual void transfer(const std::vector<Xfer> &xs) = 0;
+    // vals[i] = device pointer of local rank i; on return every one holds the sum over all ranks
+    virtual void allreduce_sum(const std::vector<double *> &vals, int n) = 0;
+};
+
+class EmuComm : public Comm {
+public:
+    explicit EmuComm(int g) { world = g; for (int r = 0; r < g; ++r) local.push_back(r); }
+    void transfer(const std::vector<Xfer> &xs) override
+    {
+        for (const Xfer &x : xs)
+            if (x.count) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream), "emu transfer");
+    }
+    void allreduce_sum(const std::vector<double *> &vals, int n) override
+    {
+        std::vector<double> acc((size_t)n, 0.0), tmp((size_t)n);
+        check(cudaStreamSynchronize(ctx().stream), "sync");
+        for (double *v : vals) {   // rank order: the same association every run
+            check(cudaMemcpy(tmp.data(), v, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost), "emu allreduce D2H");
+            for (int i = 0; i < n; ++i) acc[i] += tmp[i];
+        }
+        for (double *v : vals) check(cudaMemcpy(v, acc.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice), "emu allreduce H2D");
+    }
+};
+
+// ---- NCCL bound at run time
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the host program already uses, if any
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!handle) { fail(-30, std::string("cannot load libnccl.so.2: ") + dlerror()); return false; }
+#define MG_SYM(field, name) field = (decltype(field))dlsym(handle, name); if (!field) { fail(-31, "libnccl.so.2 lacks " name); return false; }
+        MG_SYM(GetUniqueId, "ncclGetUniqueId") MG_SYM(CommInitRank, "ncclCommInitRank") MG_SYM(CommDestroy, "ncclCommDestroy")
+        MG_SYM(Send, "ncclSend") MG_SYM(Recv, "ncclRecv") MG_SYM(AllReduce, "ncclAllReduce") MG_SYM(GroupStart, "ncclGroupStart")
+        MG_SYM(GroupEnd, "ncclGroupEnd") MG_SYM(GetErrorString, "ncclGetErrorString")
+#undef MG_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+class NcclComm : public Comm {
+public:
+    ncclComm_t comm = nullptr;
+    int rank = 0;
+    bool ok(ncclResult_t r, const char *what)
+    {
+        if (r == ncclSuccess) return true;
+        fail(-32, std::string(what) + ": " + g_nccl.GetErrorString(r));
+        return false;
+    }
+    void transfer(const std::vector<Xfer> &xs) override
+    {
+        ok(g_nccl.GroupStart(), "ncclGroupStart");
+        for (const Xfer &x : xs) {
+            if (!x.count) continue;
+            if (x.src_rank == rank && x.dst_rank == rank) {
+                check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream), "self transfer");
+                continue;
+            }
+            if (x.src_rank == rank) ok(g_nccl.Send(x.src, x.count, ncclDouble, x.dst_rank, comm, ctx().stream), "ncclSend");
+            if (x.dst_rank == rank) ok(g_nccl.Recv(x.dst, x.count, ncclDouble, x.src_rank, comm, ctx().stream), "ncclRecv");
+        }
+        ok(g_nccl.GroupEnd(), "ncclGroupEnd");
+    }
+    void allreduce_sum(const std::vector<double *> &vals, int n) override
+    {
+        ok(g_nccl.AllReduce(vals[0], vals[0], (size_t)n, ncclDouble, ncclSum, comm, ctx().stream), "ncclAllReduce");
+    }
+};
+std::unique_ptr<NcclComm> g_nccl_comm;
+
+// ------------------------------------------------------------------ geometry
+struct LevelGeom {
+    int N = 0;
+    bool dist = false;
+    std::vector<int> bound;   // dist: owned rows of rank k = [bound[k], bound[k+1])
+};
+
+Slab slab_of(const LevelGeom &g, int rank)
+{
+    Slab s;
+    if (!g.dist) { s.row0 = 0; s.rows = g.N; s.own_lo = 0; s.own_hi = g.N; return s; }
+    s.own_lo = g.bound[rank];
+    s.own_hi = g.bound[rank + 1];
+    s.row0 = std::max(0, s.own_lo - HALO);
+    s.rows = std::min(g.N, s.own_hi + HALO) - s.row0;
+    return s;
+}
+
+struct RankLevel {            // one rank's share of one level
+    Slab slab;
+    bool present = false;     // dist: every rank; agglomerated: rank 0 only
+    double *U = nullptr, *W = nullptr, *F = nullptr;
+    bool owns_F = true;
+};
+
+struct RankState {
+    int rank = 0;
+    std::vector<RankLevel> lv;
+    double *scal = nullptr;   // device scalars: [0] error partial, [1] final abs-diff partial
+};
+
+struct Pending { int rec; int index; };
+
+class DistCycle {
+public:
+    DistCycle(Comm &c, int threshold) : comm(c), threshold_(threshold)
+    {
+        for (int r : comm.local) {
+            RankState st;
+            st.rank = r;
+            st.scal = (double *)pool_alloc(64 * sizeof(double));
+            ranks.push_back(st);
+        }
+    }
+    ~DistCycle()
+    {
+        while (!geom.empty()) pop();
+        for (auto &st : ranks) pool_free(st.scal);
+    }
+
+    Comm &comm;
+    int threshold_;
+    std::vector<LevelGeom> geom;
+    std::vector<RankState> ranks;
+    int init_ = 1;
+
+    bool want_dist(int N) const { return comm.world > 1 && N >= threshold_; }
+
+    void push(const LevelGeom &g, double *borrowed_F = nullptr)
+    {
+        geom.push_back(g);
+        for (auto &st : ranks) {
+            RankLevel l;
+            l.slab = slab_of(g, st.rank);
+            l.present = g.dist || st.rank == 0;
+            if (l.present) {
+                const size_t bytes = (size_t)l.slab.rows * g.N * sizeof(double);
+                l.U = (double *)pool_alloc(bytes);
+                l.W = (double *)pool_alloc(bytes);
+                l.F = borrowed_F ? borrowed_F : (double *)pool_alloc(bytes);
+                l.owns_F = borrowed_F == nullptr;
+            }
+            st.lv.push_back(l);
+        }
+    }
+    void pop()
+    {
+        for (auto &st : ranks) {
+            RankLevel &l = st.lv.back();
+            pool_free(l.U); pool_free(l.W);
+            if (l.owns_F) pool_free(l.F);
+            st.lv.pop_back();
+        }
+        geom.pop_back();
+        if (geom.size() == 1) init_ = 0;
+    }
+    bool restart_top() const { return init_ == 0 && geom.size() == 1; }
+
+    // coarse geometry induced by the fine one (see the header comment)
+    bool induce(const LevelGeom &fine, int M, LevelGeom &coarse, std::string &why)
+    {
+        coarse.N = M;
+        coarse.dist = false;
+        coarse.bound.clear();
+        if (!fine.dist) return true;
+        if (!slab_pair_fusable(fine.N, M)) { why = "a distributed level needs an even size and a fusable transfer pair"; return false; }
+        if (!want_dist(M)) return true;
+        std::vector<int> b(comm.world + 1);
+        for (int k = 0; k < comm.world; ++k) b[k] = restrict_first_coarse_at_or_after(fine.N, M, fine.bound[k]);
+        b[comm.world] = M;
+        for (int k = 0; k < comm.world; ++k)
+            if (b[k + 1] - b[k] < 2 * HALO) return true;   // slabs too thin for single-neighbour halos: agglomerate
+        coarse.dist = true;
+        coarse.bound = b;
+        return true;
+    }
+
+    // ---- halo exchange of one array of level `li` (which: 0 U, 1 F)
+    void exchange(int li, int which)
+    {
+        const LevelGeom &g = geom[li];
+        if (!g.dist) return;
+        std::vector<Xfer> xs;
+        auto ptr = [&](int rank) -> double * {
+            for (auto &st : ranks)
+                if (st.rank == rank) return which == 0 ? st.lv[li].U : st.lv[li].F;
+            return nullptr;
+        };
+        const size_t N = g.N;
+        for (int k = 0; k + 1 < comm.world; ++k) {
+            if (!comm.is_local(k) && !comm.is_local(k + 1)) continue;
+            const Slab a = slab_of(g, k), b = slab_of(g, k + 1);
+            double *pa = ptr(k), *pb = ptr(k + 1);
+            // rank k's last HALO owned rows -> rank k+1's lower halo
+            const int up_lo = std::max(a.own_hi - HALO, b.row0);
+            xs.push_back({k, k + 1, pa ? pa + (size_t)(up_lo - a.row0) * N : nullptr, pb ? pb + (size_t)(up_lo - b.row0) * N : nullptr,
+                          (size_t)(a.own_hi - up_lo) * N});
+            // rank k+1's first HALO owned rows -> rank k's upper halo
+            const int dn_hi = std::min(b.own_lo + HALO, a.row0 + a.rows);
+            xs.push_back({k + 1, k, pb ? pb + (size_t)(b.own_lo - b.row0) * N : nullptr, pa ? pa + (size_t)(b.own_lo - a.row0) * N : nullptr,
+                          (size_t)(dn_hi - b.own_lo) * N});
+        }
+        comm.transfer(xs);
+    }
+
+    void zero(double *p, const Slab &s, int N) { check(cudaMemsetAsync(p, 0, (size_t)s.rows * N * sizeof(double), ctx().stream), "memset"); }
+
+    // sum the ranks' partials at scal[idx]; every local rank ends with the global sum
+    void allreduce(int idx)
+    {
+        if (comm.world == 1) return;
+        std::vector<double *> v;
+        for (auto &st : ranks) v.push_back(st.scal + idx);
+        comm.allreduce_sum(v, 1);
+    }
+};
+
+// Top-level source slab kept between calls (MG_RUN_SKIP_SOURCE): benchmarks and host-buffer callers
+// generate / upload F once instead of once per cycle.
+struct SourceCache {
+    int N = 0, world = 0, rank = -1, row0 = 0, rows = 0;
+    double L = 0, min_x = 0, min_y = 0;
+    double *F = nullptr;
+    bool from_host = false;
+};
+SourceCache g_src;
+
+const char *kRestrictArt = "             *\n             |\n Restriction |\n             |\n             *\n";
+const char *kProlongArt = "             *\n             |\nProlongation |\n             |\n             *\n";
+
+int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec *recs, int max_recs, mgCycleResult *res,
+             double *U_host_full, double *U_host_own, int *own_lo_out, int *own_hi_out)
+{
+    std::ifstream f(path);
+    if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
+    double L, min_x, min_y;
+    int con_step, con_N, N_max, N_min;
+    f >> L >> min_x >> min_y >> con_step >> con_N >> N_max >> N_min;
+    if (!f) return 2;
+    std::vector<int> ladder;
+    if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
+    if (con_N == 2) for (int n = N_max; n >= N_min; --n) ladder.push_back(n);
+    size_t pos = 0;
+    const bool quiet = (flags & MG_RUN_QUIET) != 0 || !comm.is_local(0);
+
+    DistCycle cy(comm, threshold);
+    Context &c = ctx();
+    {
+        LevelGeom g;
+        g.N = N_max;
+        g.dist = cy.want_dist(N_max) && N_max % 2 == 0 && N_max / comm.world >= 2 * HALO;
+        if (g.dist)
+            for (int k = 0; k <= comm.world; ++k) g.bound.push_back((int)((long long)N_max * k / comm.world));
+        // one-rank-per-process runs may keep the top-level source slab between calls
+        const bool cacheable = (flags & MG_RUN_SKIP_SOURCE) && cy.ranks.size() == 1;
+        double *borrowed = nullptr;
+        if (cacheable) {
+            const Slab s0 = slab_of(g, cy.ranks[0].rank);
+            const bool hit = g_src.F && g_src.N == N_max && g_src.world == comm.world && g_src.rank == cy.ranks[0].rank &&
+                             g_src.row0 == s0.row0 && g_src.rows == s0.rows &&
+                             (g_src.from_host || (g_src.L == L && g_src.min_x == min_x && g_src.min_y == min_y));
+            if (!hit && (g.dist || cy.ranks[0].rank == 0)) {
+                if (g_src.F) pool_free(g_src.F);
+                g_src = SourceCache();
+                g_src.F = (double *)pool_alloc((size_t)s0.rows * N_max * sizeof(double));
+                g_src.N = N_max; g_src.world = comm.world; g_src.rank = cy.ranks[0].rank; g_src.row0 = s0.row0; g_src.rows = s0.rows;
+                g_src.L = L; g_src.min_x = min_x; g_src.min_y = min_y;
+                launch_source(N_max, L, g_src.F, min_x, min_y, false, s0.row0, s0.rows);
+            }
+            if (g.dist || cy.ranks[0].rank == 0) borrowed = g_src.F;
+        }
+        cy.push(g, borrowed);
+        if (!borrowed)
+            for (auto &st : cy.ranks) {
+                RankLevel &l = st.lv[0];
+                if (l.present) launch_source(N_max, L, l.F, min_x, min_y, false, l.slab.row0, l.slab.rows);   // halo rows computed locally
+            }
+    }
+    check(cudaStreamSynchronize(c.stream), "sync");
+
+    // error scalars: device -> pinned ring, resolved after the final sync
+    std::vector<Pending> pending;
+    int n_recs = 0, slot = 0;
+    auto record = [&](int node, int N, int steps, double err) {
+        const int r = n_recs++;
+        if (recs && r < max_recs) { recs[r].node = node; recs[r].N = N; recs[r].steps = steps; recs[r].err = err; }
+        return r;
+    };
+    // Pending.rec >= 0: a raw red-parity sum (distributed node) or a GS iteration count;
+    // Pending.rec < 0 (-1-rec): an already normalised error from a single-GPU node on rank 0
+    auto harvest = [&]() {
+        check(cudaStreamSynchronize(c.stream), "sync");
+        for (const Pending &p : pending) {
+            const double v = c.slots_host[p.index];
+            const int rec = p.rec < 0 ? -1 - p.rec : p.rec;
+            if (!recs || rec >= max_recs) continue;
+            if (recs[rec].node == 0) recs[rec].steps = (int)v;
+            else if (p.rec < 0) recs[rec].err = v;
+            else { const double N = recs[rec].N; recs[rec].err = (v + v) / N / N; }   // (sum1+sum2)/N/N, :621-622
+        }
+        pending.clear();
+        slot = 0;
+    };
+    auto defer_scalar = [&](int rec, const double *dev_value) {   // async copy of a device scalar into the pinned ring
+        if (slot >= MG_SCALAR_SLOTS - 8) harvest();
+        check(cudaMemcpyAsync(c.slots_host + slot, dev_value, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H scalar");
+        pending.push_back({rec, slot++});
+    };
+
+    // one node's smoothing on a distributed level: `step` sweeps (or the trigger loop), optional
+    // restriction into the next level; returns sweeps done and records the error
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    const long long launches0 = c.launches;
+    const auto wall0 = std::chrono::steady_clock::now();
+    cudaEventRecord(ev0, c.stream);
+
+    int rc = 0, node = 0;
+    std::string why;
+    while (f >> node) {
+        if (node == 2) break;
+        if (c.err_code) { rc = 10; break; }
+        if (node == -1) {
+            int step, next_N;
+            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
+            if (con_N == 0) { if (!(f >> next_N)) { rc = 3; break; } }
+            else { if (pos + 1 >= ladder.size()) { rc = 4; break; } next_N = ladder[++pos]; }
+            if (step == 0) continue;
+            const int li = (int)cy.geom.size() - 1;
+            const LevelGeom fine = cy.geom[li];
+            const bool zero_init = !cy.restart_top();
+            LevelGeom coarse;
+            if (!cy.induce(fine, next_N, coarse, why)) { fail(-40, why); rc = 20; break; }
+            cy.push(coarse);
+
+            if (!fine.dist) {   // agglomerated: the single-GPU fused node on rank 0
+                for (auto &st : cy.ranks) {
+                    if (st.rank != 0) continue;
+                    RankLevel &l = st.lv[li], &nl = st.lv[li + 1];
+                    int done = step;
+                    if (step > 0) {
+                        double *r = down_leg(fine.N, L, l.U, l.W, l.F, step, zero_init, next_N, nl.F, nullptr);
+                        if (r != l.U) std::swap(l.U, l.W);
+                        // down_leg leaves (S+S)/N/N in dev_scalar; undo to the raw convention: store e*N*N/2
+                        const int rr = record(-1, fine.N, step, 0.0);
+                        if (slot >= MG_SCALAR_SLOTS - 8) harvest();
+                        check(cudaMemcpyAsync(c.slots_host + slot, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+                        pending.push_back({-1 - rr, slot++});
+                    } else {    // trigger loop
+                        if (zero_init) cy.zero(l.U, l.slab, fine.N);
+                        double slope = TRIGGER + 1.0, prev = 0.0, err = 0.0;
+                        done = 0;
+                        while (slope > TRIGGER) {
+                            double *r = smooth_out_of_place(fine.N, L, l.U, l.W, l.U, l.F, 1, false, c.dev_scalar, nullptr);
+                            if (r != l.U) std::swap(l.U, l.W);
+                            check(cudaMemcpyAsync(&err, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+                            check(cudaStreamSynchronize(c.stream), "sync");
+                            ++done;
+                            if (done > 1) slope = std::fabs(err - prev);
+                            prev = err;
+                            if (c.err_code) break;
+                        }
+                        down_leg(fine.N, L, l.U, l.W, l.F, 0, false, next_N, nl.F, nullptr);
+                        record(-1, fine.N, done, err);
+                    }
+                }
+                if (!comm.is_local(0) && step > 0) record(-1, fine.N, step, 0.0);
+                if (!comm.is_local(0) && step < 0) record(-1, fine.N, 0, 0.0);
+                if (!quiet) fputs(kRestrictArt, stdout);
+                continue;
+            }
+
+            // ---- distributed fine level
+            // F_c target per rank: the coarse slab's F if the coarse level is distributed, else a
+            // temporary holding exactly the rank's coarse rows (rank 0 writes into the full array)
+            std::vector<int> cb(comm.world + 1);
+            for (int k = 0; k < comm.world; ++k) cb[k] = restrict_first_coarse_at_or_after(fine.N, next_N, fine.bound[k]);
+            cb[comm.world] = next_N;
+            std::vector<double *> fc_tmp(cy.ranks.size(), nullptr);
+            std::vector<Slab> fc_slab(cy.ranks.size());
+            for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                RankState &st = cy.ranks[i];
+                if (coarse.dist) { fc_slab[i] = st.lv[li + 1].slab; continue; }
+                if (st.rank == 0) { fc_slab[i] = st.lv[li + 1].slab; continue; }
+                fc_slab[i].row0 = fc_slab[i].own_lo = cb[st.rank];
+                fc_slab[i].own_hi = cb[st.rank + 1];
+                fc_slab[i].rows = cb[st.rank + 1] - cb[st.rank];
+                fc_tmp[i] = (double *)pool_alloc((size_t)std::max(1, fc_slab[i].rows) * next_N * sizeof(double));
+            }
+            auto fc_ptr = [&](size_t i) { return fc_tmp[i] ? fc_tmp[i] : cy.ranks[i].lv[li + 1].F; };
+
+            int done = 0;
+            double err_host = 0.0;
+            if (step > 0) {
+                // passes of at most 3 sweeps; halos of the pass input must be current
+                const int n_pass = (step + 2) / 3;
+                for (int k = 0; k < n_pass; ++k) {
+                    const int S = step / n_pass + (k < step % n_pass ? 1 : 0);
+                    const bool first = k == 0, last = k + 1 == n_pass;
+                    const int in_mode = (first && zero_init) ? 1 : 0;
+                    if (in_mode == 0) cy.exchange(li, 0);
+                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                        RankLevel &l = cy.ranks[i].lv[li];
+                        slab_pass(fine.N, L, S, in_mode, l.U, l.F, l.W, l.slab, last, cy.ranks[i].scal, next_N,
+                                  last ? fc_ptr(i) : nullptr, last ? &fc_slab[i] : nullptr, 0, nullptr, nullptr);
+                        std::swap(l.U, l.W);
+                    }
+                }
+                done = step;
+                cy.allreduce(0);
+                const int rr = record(-1, fine.N, step, 0.0);
+                defer_scalar(rr, cy.ranks[0].scal);
+            } else {   // trigger loop: the scalar is needed after every sweep
+                double slope = TRIGGER + 1.0, prev = 0.0;
+                bool first = true;
+                while (slope > TRIGGER) {
+                    const int in_mode = (first && zero_init) ? 1 : 0;
+                    if (in_mode == 0) cy.exchange(li, 0);
+                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                        RankLevel &l = cy.ranks[i].lv[li];
+                        slab_pass(fine.N, L, 1, in_mode, l.U, l.F, l.W, l.slab, true, cy.ranks[i].scal, 0, nullptr, nullptr, 0, nullptr, nullptr);
+                        std::swap(l.U, l.W);
+                    }
+                    cy.allreduce(0);
+                    double s = 0.0;
+                    check(cudaMemcpyAsync(&s, cy.ranks[0].scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+                    check(cudaStreamSynchronize(c.stream), "sync");
+                    err_host = (s + s) / fine.N / fine.N;
+                    ++done;
+                    if (done > 1) slope = std::fabs(err_host - prev);
+                    prev = err_host;
+                    first = false;
+                    if (c.err_code) break;
+                }
+                cy.exchange(li, 0);
+                for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                    RankLevel &l = cy.ranks[i].lv[li];
+                    slab_pass(fine.N, L, 0, 0, l.U, l.F, nullptr, l.slab, false, nullptr, next_N, fc_ptr(i), &fc_slab[i], 0, nullptr, nullptr);
+                }
+                record(-1, fine.N, done, err_host);
+            }
+            // ---- make the coarse source complete
+            if (coarse.dist) {
+                cy.exchange(li + 1, 1);
+            } else {           // gather the slabs' coarse rows into rank 0's full grid
+                std::vector<Xfer> xs;
+                for (int k = 1; k < comm.world; ++k) {
+                    const double *src = nullptr;
+                    double *dst = nullptr;
+                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                        if (cy.ranks[i].rank == k) src = fc_tmp[i];
+                        if (cy.ranks[i].rank == 0) dst = cy.ranks[i].lv[li + 1].F + (size_t)cb[k] * next_N;
+                    }
+                    if (!comm.is_local(k) && !comm.is_local(0)) continue;
+                    xs.push_back({k, 0, src, dst, (size_t)(cb[k + 1] - cb[k]) * next_N});
+                }
+                comm.transfer(xs);
+            }
+            for (double *p : fc_tmp) pool_free(p);
+            if (!quiet) fputs(kRestrictArt, stdout);
+        } else if (node == 0) {
+            double target; int option;
+            if (!(f >> target >> option)) { rc = 3; break; }
+            const int li = (int)cy.geom.size() - 1;
+            if (cy.geom[li].dist) { fail(-41, "the exact solver runs on an agglomerated level: lower the coarsest size or raise the threshold"); rc = 21; break; }
+            const int rr = record(0, cy.geom[li].N, -1, 0.0);
+            for (auto &st : cy.ranks) {
+                if (st.rank != 0) continue;
+                RankLevel &l = st.lv[li];
+                if (slot >= MG_SCALAR_SLOTS - 8) harvest();
+                if (option == 0) launch_inverse_matrix(cy.geom[li].N, L, l.U, l.F);
+                else if (option == 1) {
+                    launch_gauss_seidel(cy.geom[li].N, L, l.U, l.F, target, c.slots_dev + slot);
+                    pending.push_back({rr, slot++});
+                }
+            }
+            if (!quiet) {
+                printf("          ~Exact Solver~\nCurrent Grid Size N = %d\n", cy.geom[li].N);
+                if (option == 0) printf("   Use Exact Solver = Inverse Matrix\n");
+                if (option == 1) printf("   Use Exact Solver = GaussSeidel Even / Odd\n");
+                printf("       Target Error = %.3e\n", target);
+            }
+        } else if (node == 1) {
+            int step;
+            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
+            if (con_N != 0 && pos > 0) --pos;
+            if (cy.geom.size() < 2) { rc = 5; break; }
+            const int lc = (int)cy.geom.size() - 1, lf = lc - 1;
+            const LevelGeom coarse = cy.geom[lc], fine = cy.geom[lf];
+
+            if (!fine.dist) {
+                for (auto &st : cy.ranks) {
+                    if (st.rank != 0) continue;
+                    RankLevel &l = st.lv[lf], &cl = st.lv[lc];
+                    double *r = up_leg(coarse.N, cl.U, fine.N, L, l.U, l.W, l.F, step > 0 ? step : 0, nullptr);
+                    if (r != l.U) std::swap(l.U, l.W);
+                    if (step > 0) {
+                        const int rr = record(1, fine.N, step, 0.0);
+                        if (slot >= MG_SCALAR_SLOTS - 8) harvest();
+                        check(cudaMemcpyAsync(c.slots_host + slot, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+                        pending.push_back({-1 - rr, slot++});
+                    } else if (step < 0) {
+                        double slope = TRIGGER + 1.0, prev = 0.0, err = 0.0;
+                        int done = 0;
+                        while (slope > TRIGGER) {
+                            double *q = smooth_out_of_place(fine.N, L, l.U, l.W, l.U, l.F, 1, false, c.dev_scalar, nullptr);
+                            if (q != l.U) std::swap(l.U, l.W);
+                            check(cudaMemcpyAsync(&err, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+                            check(cudaStreamSynchronize(c.stream), "sync");
+                            ++done;
+                            if (done > 1) slope = std::fabs(err - prev);
+                            prev = err;
+                            if (c.err_code) break;
+                        }
+                        record(1, fine.N, done, err);
+                    } else record(1, fine.N, 0, 0.0);
+                }
+                if (!comm.is_local(0)) record(1, fine.N, step > 0 ? step : 0, 0.0);
+                if (!quiet) fputs(kProlongArt, stdout);
+                cy.pop();
+                continue;
+            }
+
+            // ---- distributed fine level: U_c rows with halo on every rank, current U_f halos
+            std::vector<double *> uc_tmp(cy.ranks.size(), nullptr);
+            std::vector<Slab> uc_slab(cy.ranks.size());
+            if (coarse.dist) {
+                cy.exchange(lc, 0);
+                for (size_t i = 0; i < cy.ranks.size(); ++i) uc_slab[i] = cy.ranks[i].lv[lc].slab;
+            } else {
+                std::vector<int> cb(comm.world + 1);
+                for (int k = 0; k < comm.world; ++k) cb[k] = restrict_first_coarse_at_or_after(fine.N, coarse.N, fine.bound[k]);
+                cb[comm.world] = coarse.N;
+                std::vector<Xfer> xs;
+                const double *full = nullptr;
+                for (auto &st : cy.ranks) if (st.rank == 0) full = st.lv[lc].U;
+                for (int k = 0; k < comm.world; ++k) {
+                    Slab s;
+                    s.own_lo = cb[k]; s.own_hi = cb[k + 1];
+                    s.row0 = std::max(0, cb[k] - HALO);
+                    s.rows = std::min(coarse.N, cb[k + 1] + HALO) - s.row0;
+                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                        if (cy.ranks[i].rank != k) continue;
+                        if (k == 0) { uc_slab[i] = cy.ranks[i].lv[lc].slab; continue; }
+                        uc_slab[i] = s;
+                        uc_tmp[i] = (double *)pool_alloc((size_t)s.rows * coarse.N * sizeof(double));
+                    }
+                    if (k == 0 || (!comm.is_local(k) && !comm.is_local(0))) continue;
+                    double *dst = nullptr;
+                    for (size_t i = 0; i < cy.ranks.size(); ++i) if (cy.ranks[i].rank == k) dst = uc_tmp[i];
+                    xs.push_back({0, k, full ? full + (size_t)s.row0 * coarse.N : nullptr, dst, (size_t)s.rows * coarse.N});
+                }
+                comm.transfer(xs);
+            }
+            auto uc_ptr = [&](size_t i) -> const double * { return uc_tmp[i] ? uc_tmp[i] : cy.ranks[i].lv[lc].U; };
+            cy.exchange(lf, 0);
+
+            int done = 0;
+            double err_host = 0.0;
+            const int fixed = step > 0 ? step : 0;
+            const int n_pass = std::max(1, (fixed + 2) / 3);
+            for (int k = 0; k < n_pass; ++k) {
+                const int S = fixed / n_pass + (k < fixed % n_pass ? 1 : 0);
+                const bool first = k == 0, last = k + 1 == n_pass;
+                if (!first) cy.exchange(lf, 0);
+                for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                    RankLevel &l = cy.ranks[i].lv[lf];
+                    slab_pass(fine.N, L, S, first ? 2 : 0, l.U, l.F, l.W, l.slab, last && step > 0, cy.ranks[i].scal, 0, nullptr, nullptr,
+                              coarse.N, first ? uc_ptr(i) : nullptr, first ? &uc_slab[i] : nullptr);
+                    std::swap(l.U, l.W);
+                }
+            }
+            if (step > 0) {
+                done = step;
+                cy.allreduce(0);
+                const int rr = record(1, fine.N, step, 0.0);
+                defer_scalar(rr, cy.ranks[0].scal);
+            } else if (step < 0) {
+                double slope = TRIGGER + 1.0, prev = 0.0;
+                while (slope > TRIGGER) {
+                    cy.exchange(lf, 0);
+                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                        RankLevel &l = cy.ranks[i].lv[lf];
+                        slab_pass(fine.N, L, 1, 0, l.U, l.F, l.W, l.slab, true, cy.ranks[i].scal, 0, nullptr, nullptr, 0, nullptr, nullptr);
+                        std::swap(l.U, l.W);
+                    }
+                    cy.allreduce(0);
+                    double s = 0.0;
+                    check(cudaMemcpyAsync(&s, cy.ranks[0].scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+                    check(cudaStreamSynchronize(c.stream), "sync");
+                    err_host = (s + s) / fine.N / fine.N;
+                    ++done;
+                    if (done > 1) slope = std::fabs(err_host - prev);
+                    prev = err_host;
+                    if (c.err_code) break;
+                }
+                record(1, fine.N, done, err_host);
+            } else record(1, fine.N, 0, 0.0);
+            for (double *p : uc_tmp) pool_free(p);
+            if (!quiet) fputs(kProlongArt, stdout);
+            cy.pop();
+        } else { rc = 6; break; }
+    }
+    cudaEventRecord(ev1, c.stream);
+    harvest();
+    const auto wall1 = std::chrono::steady_clock::now();
+    if (c.err_code && rc == 0) rc = 10;
+
+    if (res) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        res->time_ms = ms;
+        res->wall_ms = std::chrono::duration<double, std::milli>(wall1 - wall0).count();
+        res->launches = (int)(c.launches - launches0);
+        res->n_recs = n_recs < max_recs ? n_recs : max_recs;
+        res->N = N_max;
+        res->mg_error = 0.0;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+
+    if (rc == 0) {
+        const LevelGeom &g = cy.geom[0];
+        // ---- final report: mean |analytic - U| (:434-445), slab partial sums all-reduced
+        if (res && !(flags & MG_RUN_NO_FINAL_ERROR)) {
+            for (auto &st : cy.ranks) {
+                RankLevel &l = st.lv[0];
+                check(cudaMemsetAsync(st.scal + 1, 0, sizeof(double), c.stream), "memset");
+                if (!l.present) continue;
+                launch_source(g.N, L, l.W, min_x, min_y, true, l.slab.row0, l.slab.rows);
+                const size_t off = (size_t)(l.slab.own_lo - l.slab.row0) * g.N, cnt = (size_t)(l.slab.own_hi - l.slab.own_lo) * g.N;
+                launch_mean_abs_diff(cnt, l.W + off, l.U + off, 1.0, st.scal + 1);
+            }
+            if (g.dist) cy.allreduce(1);
+            double s = 0.0;
+            check(cudaMemcpyAsync(&s, cy.ranks[0].scal + 1, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+            check(cudaStreamSynchronize(c.stream), "sync");
+            res->mg_error = s / ((double)g.N * (double)g.N);
+        }
+        // ---- solution out
+        for (auto &st : cy.ranks) {
+            RankLevel &l = st.lv[0];
+            if (!l.present) continue;
+            const size_t off = (size_t)(l.slab.own_lo - l.slab.row0) * g.N, cnt = (size_t)(l.slab.own_hi - l.slab.own_lo) * g.N;
+            if (U_host_full) check(cudaMemcpyAsync(U_host_full + (size_t)l.slab.own_lo * g.N, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
+            if (U_host_own) check(cudaMemcpyAsync(U_host_own, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
+            if (own_lo_out) *own_lo_out = l.slab.own_lo;
+            if (own_hi_out) *own_hi_out = l.slab.own_hi;
+        }
+        check(cudaStreamSynchronize(c.stream), "sync");
+        if (!quiet && res) {
+            printf("\n\n===== Final Result =====\n    Error = %lf\nTime Used = %lf (ms)\n", res->mg_error, res->wall_ms);
+        }
+    }
+    return rc;
+}
+
+}  // namespace
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags, double *U_host, mgTraceRec *recs,
+                          int max_recs, mgCycleResult *res)
+{
+    if (!ensure_ready()) return 10;
+    if (world < 1) return 11;
+    EmuComm comm(world);
+    return run_dist(comm, path, threshold, flags, recs, max_recs, res, U_host, nullptr, nullptr, nullptr);
+}
+
+int mgDistUniqueId(void *out128)
+{
+    if (!g_nccl.load()) return 1;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { fail(-33, "ncclGetUniqueId failed"); return 2; }
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+int mgDistInit(int rank, int world, const void *id128)
+{
+    if (!ensure_ready()) return 10;
+    if (!g_nccl.load()) return 1;
+    if (g_nccl_comm) return 0;
+    std::unique_ptr<NcclComm> cm(new NcclComm());
+    cm->world = world;
+    cm->rank = rank;
+    cm->local = {rank};
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    if (!cm->ok(g_nccl.CommInitRank(&cm->comm, world, id, rank), "ncclCommInitRank")) return 2;
+    g_nccl_comm = std::move(cm);
+    return 0;
+}
+
+int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, int *own_hi)
+{
+    if (!g_nccl_comm) { fail(-34, "mgDistSourceSlab: call mgDistInit first"); return 12; }
+    LevelGeom g;
+    g.N = N;
+    const int world = g_nccl_comm->world;
+    g.dist = world > 1 && N >= threshold && N % 2 == 0 && N / world >= 2 * HALO;
+    if (g.dist)
+        for (int k = 0; k <= world; ++k) g.bound.push_back((int)((long long)N * k / world));
+    const Slab s = slab_of(g, g_nccl_comm->rank);
+    const bool present = g.dist || g_nccl_comm->rank == 0;
+    *row0 = s.row0; *rows = present ? s.rows : 0; *own_lo = s.own_lo; *own_hi = present ? s.own_hi : s.own_lo;
+    return 0;
+}
+
+int mgDistUploadSource(int N, int threshold, const double *F_slab_host)
+{
+    if (!ensure_ready()) return 10;
+    int row0, rows, lo, hi;
+    if (mgDistSourceSlab(N, threshold, &row0, &rows, &lo, &hi)) return 12;
+    if (rows == 0) return 0;
+    const bool match = g_src.F && g_src.N == N && g_src.world == g_nccl_comm->world && g_src.rank == g_nccl_comm->rank &&
+                       g_src.row0 == row0 && g_src.rows == rows;
+    if (!match) {
+        if (g_src.F) pool_free(g_src.F);
+        g_src = SourceCache();
+        g_src.F = (double *)pool_alloc((size_t)rows * N * sizeof(double));
+        g_src.N = N; g_src.world = g_nccl_comm->world; g_src.rank = g_nccl_comm->rank; g_src.row0 = row0; g_src.rows = rows;
+    }
+    g_src.from_host = true;
+    check(cudaMemcpyAsync(g_src.F, F_slab_host, (size_t)rows * N * sizeof(double), cudaMemcpyHostToDevice, ctx().stream), "H2D source slab");
+    return 0;
+}
+
+int mgDistDownloadSource(int N, double *F_slab_host)
+{
+    if (!ensure_ready() || !g_src.F || g_src.N != N) return 1;
+    check(cudaMemcpyAsync(F_slab_host, g_src.F, (size_t)g_src.rows * N * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream), "D2H source slab");
+    check(cudaStreamSynchronize(ctx().stream), "sync");
+    return 0;
+}
+
+void mgDistShutdown(void)
+{
+    if (g_nccl_comm) {
+        cudaStreamSynchronize(ctx().stream);
+        g_nccl.CommDestroy(g_nccl_comm->comm);
+        g_nccl_comm.reset();
+    }
+}
+
+int mgDistRunCycleFile(const char *path, int threshold, int flags, double *U_own_host, int *own_lo, int *own_hi,
+                       mgTraceRec *recs, int max_recs, mgCycleResult *res)
+{
+    if (!ensure_ready()) return 10;
+    if (!g_nccl_comm) { fail(-34, "mgDistRunCycleFile: call mgDistInit first"); return 12; }
+    return run_dist(*g_nccl_comm, path, threshold, flags, recs, max_recs, res, nullptr, U_own_host, own_lo, own_hi);
+}
+
+}  // extern "C"

@@ -19,6 +19,7 @@ struct FusedRestrictTable {
     int *f2c = nullptr;     // device [N]
     double *rw = nullptr;   // device [M]
     double2 *rrow = nullptr;  // device [N]: {coarse row or -1, its weight}
+    std::vector<int> fine_of_coarse;   // host [M]: the fine row whose pair (f, f+1) produces coarse row c
 };
 std::map<std::pair<int, int>, FusedRestrictTable> g_restrict_tables;
 int g_force_H = 0;
@@ -58,6 +59,9 @@ const FusedRestrictTable &fused_restrict_table(int N, int M)
             good = good && check(cudaMemcpy(t.f2c, f2c.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice), "H2D f2c");
             good = good && check(cudaMemcpy(t.rw, rw.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice), "H2D rw");
             t.usable = good;
+            t.fine_of_coarse.assign((size_t)M, 0);
+            for (int f = 0; f < N; ++f)
+                if (f2c[f] >= 0) t.fine_of_coarse[f2c[f]] = f;
         }
     }
     return g_restrict_tables.emplace(std::make_pair(N, M), t).first->second;
@@ -74,16 +78,17 @@ void launch_stream(StreamParams &p)
     // cost (2S+3)/H of extra work, so at least 32 rows), otherwise as many tasks as 16-row
     // segments allow.
     const int resident_warps = 2 * c.sm_count * STREAM_WARPS;
+    const int own_rows = p.own_hi - p.own_lo;
     int H = g_force_H;
     if (H <= 0) {
-        const long long row_strips = (long long)N * p.n_strips;
+        const long long row_strips = (long long)own_rows * p.n_strips;
         H = (int)(row_strips / (4LL * resident_warps));
         H = std::max(32, std::min(256, H));
-        if ((long long)((N + H - 1) / H) * p.n_strips < resident_warps) H = std::max(16, (int)(row_strips / resident_warps));
+        if ((long long)((own_rows + H - 1) / H) * p.n_strips < resident_warps) H = std::max(16, (int)(row_strips / resident_warps));
         H = std::min(256, (H + 7) / 8 * 8);
     }
     p.H = H;
-    p.n_segs = (N + H - 1) / H;
+    p.n_segs = (own_rows + H - 1) / H;
     p.n_tasks = p.n_strips * p.n_segs;
     const int blocks = std::max(1, std::min(2 * c.sm_count, (p.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS));
     if (ERR) p.partials = partials_buf((size_t)p.n_tasks);
@@ -150,6 +155,9 @@ struct LegSpec {
     int M = 0;
     double *Fc = nullptr;
     double *err_dev = nullptr, *err_slot = nullptr;
+    // row slab (defaults = the whole grid, filled in by run_leg when rows == 0)
+    int row0 = 0, rows = 0, own_lo = 0, own_hi = 0, fc_row0 = 0, uc_row0 = 0, uc_rows = 0;
+    bool raw_sum = false;
 };
 
 // Runs the passes of one leg on even N.  The first pass reads `in` (never written, unused for
@@ -167,6 +175,14 @@ double *run_leg(int N, double L, const double *in, double *a, double *b, const d
         const bool first = k == 0, last = k + 1 == passes.size();
         StreamParams p{};
         p.N = N;
+        p.row0 = spec.rows ? spec.row0 : 0;
+        p.rows = spec.rows ? spec.rows : N;
+        p.own_lo = spec.rows ? spec.own_lo : 0;
+        p.own_hi = spec.rows ? spec.own_hi : N;
+        p.fc_row0 = spec.fc_row0;
+        p.uc_row0 = spec.uc_row0;
+        p.uc_rows = spec.uc_rows ? spec.uc_rows : spec.Nc;
+        p.raw_sum = spec.raw_sum ? 1 : 0;
         p.h2 = sp.h2;
         p.inv_h2 = sp.inv_h2;
         p.F = F;
@@ -215,6 +231,66 @@ double *run_leg(int N, double L, const double *in, double *a, double *b, const d
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------ row-slab passes (multi-GPU)
+bool slab_pair_fusable(int N, int M)
+{
+    return streamable(N) && M >= 3 && fused_restrict_table(N, M).usable && (double)(N - 1) >= 1.2 * (double)(M - 1);
+}
+
+int restrict_first_coarse_at_or_after(int N, int M, int fine_row)
+{
+    const FusedRestrictTable &t = fused_restrict_table(N, M);
+    int c = 0;
+    while (c < M && t.fine_of_coarse[c] < fine_row) ++c;   // fine_of_coarse is strictly increasing
+    return c;
+}
+
+void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
+               bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
+               const Slab *coarse_in)
+{
+    const Spacing sp = spacing(N, L);
+    StreamParams p{};
+    p.N = N;
+    p.row0 = fine.row0;
+    p.rows = fine.rows;
+    p.own_lo = fine.own_lo;
+    p.own_hi = fine.own_hi;
+    p.raw_sum = 1;
+    p.h2 = sp.h2;
+    p.inv_h2 = sp.inv_h2;
+    p.F = F;
+    p.Uin = Uin;
+    p.Uout = Uout;
+    int mode = want_err ? 1 : 0;
+    if (want_err) p.err_dev = raw_err_dev;
+    if (coarse_out) {
+        const FusedRestrictTable &t = fused_restrict_table(N, M);
+        mode = 2;
+        p.M = M;
+        p.Fc = Fc;
+        p.fc_row0 = coarse_out->row0;
+        p.f2c = t.f2c;
+        p.rw = t.rw;
+        p.rrow = t.rrow;
+        p.err_dev = want_err ? raw_err_dev : nullptr;
+    }
+    if (in_mode == IN_PROLONG) {
+        const ProlongTable &t = prolong_table(Nc, N);
+        p.Nc = Nc;
+        p.Uc = Uc;
+        p.uc_row0 = coarse_in->row0;
+        p.uc_rows = coarse_in->rows;
+        p.row_cell = t.row_cell;
+        p.col_cell = t.col_cell;
+        p.row_w = t.row_w;
+        p.col_w = t.col_w;
+        p.c_dx = 1.0 / (double)(Nc - 1);
+        p.inv_c_dx = 1.0 / p.c_dx;
+    }
+    launch_stream_any(S, in_mode, mode, p);
+}
 
 void fused_init()
 {

@@ -24,4 +24,20 @@ double *down_leg(int N, double L, double *U, double *U_work, const double *F, in
 double *up_leg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, const double *F, int step,
                double *err_slot);
 
+// ------------------------------------------------------------------ row slabs (multi-GPU, mg_dist.cu)
+// A slab holds global rows [row0, row0+rows) of an N-column grid and owns [own_lo, own_hi).
+struct Slab {
+    int row0 = 0, rows = 0, own_lo = 0, own_hi = 0;
+};
+// even N, injective restriction map N -> M, prolongation ratio the staged coarse row can hold
+bool slab_pair_fusable(int N, int M);
+// smallest coarse row whose lower fine row (floor map of doRestriction) is >= fine_row; M if none
+int restrict_first_coarse_at_or_after(int N, int M, int fine_row);
+// One streaming pass (S <= 3 sweeps) on a slab.  in_mode: 0 load, 1 zero, 2 prolong (+add).
+// want_err: the slab's plain red-parity sum goes to *raw_err_dev.  coarse_out != null: restrict
+// the negated residual into the local F_c array of that coarse slab.  coarse_in: the local U_c.
+void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
+               bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
+               const Slab *coarse_in);
+
 }  // namespace mg

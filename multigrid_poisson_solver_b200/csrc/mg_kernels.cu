@@ -47,10 +47,10 @@ Tiling tiling(int N, int rows = ROWS) { return {(N + TX - 1) / TX, (N + rows - 1
 // MG_solver_CPU.cpp:468-493 (source), :525-548 (analytic).  exp() is CUDA's (<= 1 ulp from glibc).
 template <bool ANALYTIC>
 __global__ void __launch_bounds__(TX) k_problem(int N, int col_blocks, double h, double min_x, double min_y,
-                                                double *__restrict__ out)
+                                                double *__restrict__ out, int row0)
 {
     const int j = (blockIdx.x % col_blocks) * TX + threadIdx.x;  // ix
-    const int i = blockIdx.x / col_blocks;                       // iy
+    const int i = row0 + blockIdx.x / col_blocks;                // iy (global); the array starts at row0
     if (j >= N) return;
     double v = 0.0;
     if (i > 0 && i < N - 1 && j > 0 && j < N - 1) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(TX) k_problem(int N, int col_blocks, double h,
             v = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, x), __dsub_rn(y, 1.0)), poly), e);
         }
     }
-    out[(size_t)i * N + j] = v;
+    out[(size_t)(i - row0) * N + j] = v;
 }
 
 // ------------------------------------------------------------------ residual
@@ -307,13 +307,14 @@ __global__ void __launch_bounds__(TX) k_abs_diff(size_t n, const double *__restr
 
 // =============================================================================== launchers
 
-void launch_source(int N, double L, double *F, double min_x, double min_y, bool analytic)
+void launch_source(int N, double L, double *F, double min_x, double min_y, bool analytic, int row0, int rows)
 {
     const double h = L / (double)(N - 1);
     const int cb = (N + TX - 1) / TX;
-    const unsigned blocks = (unsigned)cb * (unsigned)N;
-    if (analytic) MG_LAUNCH(k_problem<true>, blocks, TX, 0, N, cb, h, min_x, min_y, F);
-    else          MG_LAUNCH(k_problem<false>, blocks, TX, 0, N, cb, h, min_x, min_y, F);
+    if (rows < 0) rows = N;
+    const unsigned blocks = (unsigned)cb * (unsigned)rows;
+    if (analytic) MG_LAUNCH(k_problem<true>, blocks, TX, 0, N, cb, h, min_x, min_y, F, row0);
+    else          MG_LAUNCH(k_problem<false>, blocks, TX, 0, N, cb, h, min_x, min_y, F, row0);
 }
 
 void launch_residual(int N, double inv_h2, const double *U, const double *F, double *D)

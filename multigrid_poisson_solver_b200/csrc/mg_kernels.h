@@ -15,7 +15,8 @@ struct Spacing {
 Spacing spacing(int N, double L);
 
 // ---- baseline kernels: one reference operator each
-void launch_source(int N, double L, double *F, double min_x, double min_y, bool analytic);
+// rows [row0, row0+rows) of the grid into an array that starts at row0 (rows < 0: the whole grid)
+void launch_source(int N, double L, double *F, double min_x, double min_y, bool analytic, int row0 = 0, int rows = -1);
 void launch_residual(int N, double inv_h2, const double *U, const double *F, double *D);
 void launch_add(int N, double *U1, const double *U2);
 void launch_negate(int N, double *D);

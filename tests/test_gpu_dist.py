@@ -1,0 +1,77 @@
+"""GPU suite for the row-slab multi-GPU driver, exercised on ONE GPU: all ranks are emulated in
+one process (mgDistEmuRunCycleFile), with device-to-device copies in place of NCCL.  The slab
+path must reproduce the single-GPU result bit for bit (same arithmetic per point), and its
+all-reduced errors to <= 1e-10 relative."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import multigrid_poisson_solver_b200 as m
+    m.init(0)
+    return m
+
+
+def cycle_file(text):
+    f = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False)
+    f.write(text)
+    f.close()
+    return f.name
+
+
+def compare(mg, text, world, threshold):
+    path = cycle_file(text)
+    try:
+        one = mg.run_cycle_host(path, mg.RUN_FUSED | mg.RUN_QUIET)
+        emu = mg.run_cycle_dist_emulated(path, world, threshold)
+    finally:
+        os.unlink(path)
+    assert [(t["node"], t["N"]) for t in emu["trace"]] == [(t["node"], t["N"]) for t in one["trace"]]
+    for a, b in zip(emu["trace"], one["trace"]):
+        assert a["steps"] == b["steps"], (a, b)
+        if b["node"] != 0:
+            assert a["err"] == pytest.approx(b["err"], rel=1e-10), (a, b)
+    bad = np.flatnonzero(emu["U"] != one["U"])
+    assert bad.size == 0, "U differs at %d points, first %d (row %d)" % (bad.size, bad[0], bad[0] // one["N"])
+    assert emu["mg_error"] == pytest.approx(one["mg_error"], rel=1e-10)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_vcycle_slabs_match_single_gpu(mg, world):
+    compare(mg, mg.cycles.v_cycle(1024, 8), world, 256)
+
+
+@pytest.mark.parametrize("world,threshold", [(2, 64), (4, 128), (8, 1024), (2, 2048)])
+def test_vcycle_thresholds(mg, world, threshold):
+    compare(mg, mg.cycles.v_cycle(1024, 8), world, threshold)   # (2, 2048): nothing is distributed
+
+
+def test_wcycle_slabs(mg):
+    compare(mg, mg.cycles.w_cycle(512, 8, levels=4, step=2, tol=1e-7), 4, 128)
+
+
+def test_trigger_cycle_slabs(mg):
+    compare(mg, mg.cycles.v_cycle(512, 8, step=-1), 4, 128)
+
+
+@pytest.mark.parametrize("step", [1, 2, 4, 5, 7])
+def test_multi_pass_steps(mg, step):
+    compare(mg, mg.cycles.v_cycle(512, 16, step=step), 3, 128)
+
+
+def test_restart_chain_slabs(mg):
+    compare(mg, mg.cycles.v_cycle(512, 8, step=2, cycles=2), 4, 128)
+
+
+def test_non_power_of_two_ladder(mg):
+    compare(mg, mg.cycles.v_cycle(1448, 8), 4, 300)        # 1448 -> 724 -> 362 -> 181 (odd, agglomerated)
+
+
+def test_large_grid_slabs(mg):
+    compare(mg, mg.cycles.v_cycle(4096, 8), 8, 1024)
