@@ -90,6 +90,14 @@ void launch_stream(StreamParams &p)
     p.H = H;
     p.n_segs = (own_rows + H - 1) / H;
     p.n_tasks = p.n_strips * p.n_segs;
+    // the kernel indexes every grid with GLOBAL rows: shift the bases of the local arrays
+    p.F_valid = p.F;
+    const ptrdiff_t fine_shift = (ptrdiff_t)p.row0 * N;
+    if (p.Uin) p.Uin -= fine_shift;
+    if (p.F) p.F -= fine_shift;
+    if (p.Uout) p.Uout -= fine_shift;
+    if (p.Fc) p.Fc -= (ptrdiff_t)p.fc_row0 * p.M;
+    if (p.Uc) p.Uc -= (ptrdiff_t)p.uc_row0 * p.Nc;
     const int blocks = std::max(1, std::min(2 * c.sm_count, (p.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS));
     if (ERR) p.partials = partials_buf((size_t)p.n_tasks);
     p.counter = c.counters + 8;   // [8] queue head, [9] finished warps (self-resetting)

@@ -51,6 +51,8 @@ struct StreamParams {
     int N;                  // grid size (even): columns, and rows of the GLOBAL grid
     // Row slab (multi-GPU): the arrays hold global rows [row0, row0+rows); this call owns (writes,
     // sums, restricts) global rows [own_lo, own_hi).  Single GPU: row0 = 0, rows = N, own = [0, N).
+    // ALL grid pointers below are pre-offset by the launcher so that they are indexed with GLOBAL
+    // rows (Uin/F/Uout by -row0*N, Fc by -fc_row0*M, Uc by -uc_row0*Nc): the kernel never subtracts.
     int row0, rows, own_lo, own_hi;
     int fc_row0;            // global index of local row 0 of the F_c array
     int uc_row0, uc_rows;   // global index of local row 0 of the U_c array, and its local row count
@@ -58,6 +60,7 @@ struct StreamParams {
     int H;                  // rows owned by one task
     int n_strips, n_segs, n_tasks;   // tasks (strip, row segment) are handed to warps through an atomic queue
     double h2, inv_h2;
+    const double *F_valid;  // any dereferenceable address (source operand of zero-fill copies)
     const double *Uin;      // IN_LOAD: U ; IN_PROLONG: U_f
     const double *F;
     double *Uout;
@@ -232,7 +235,6 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     const int own_r_lo = p.own_lo + seg * p.H, own_r_hi = min(own_r_lo + p.H, p.own_hi);
     const int r_first = max(0, own_r_lo - G::ROW_LEAD);
     const int r_last = min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD);
-    const int row0 = p.row0, row_end = p.row0 + p.rows;   // rows present in the local arrays
 
     // Register state.  Every index below is a compile-time constant after unrolling, so the
     // arrays live in registers and rotate by renaming, not by moves.
@@ -303,21 +305,21 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     // for the 1 node also the upper coarse row of fine row r's cell (`rq` = row_cell[r])
     auto issue = [&](int r, unsigned off, int rq) {
         if (IN != IN_ZERO) {
-            const bool ok = col_ok && r >= row0 && r < row_end;
-            cp_async16(ring_base + off, ok ? (const void *)(Up + (ptrdiff_t)(r - row0) * ldn + cx) : (const void *)Up, ok);
+            const bool ok = col_ok && r >= p.row0 && r < p.row0 + p.rows;
+            cp_async16(ring_base + off, ok ? (const void *)(Up + (ptrdiff_t)r * ldn + cx) : (const void *)p.F_valid, ok);
         }
         if (NF > 0) {
-            const bool ok = col_ok && r - 1 >= row0 && r - 1 < row_end;
-            cp_async16(ring_base + off + 512, ok ? (const void *)(Fp + (ptrdiff_t)(r - 1 - row0) * ldn + cx) : (const void *)Fp, ok);
+            const bool ok = col_ok && r - 1 >= p.row0 && r - 1 < p.row0 + p.rows;
+            cp_async16(ring_base + off + 512, ok ? (const void *)(Fp + (ptrdiff_t)(r - 1) * ldn + cx) : (const void *)p.F_valid, ok);
         }
         if (IN == IN_PROLONG) {
             const int c0 = cbase + 2 * lane;
             const bool row_ok = active && r <= N - 1;
             // rows prefetched beyond the ones a task needs may map outside the local coarse slab: clamp (never used)
-            const double *src = p.Uc + (ptrdiff_t)(row_ok ? min(max(rq + 1 - p.uc_row0, 0), p.uc_rows - 1) : 0) * p.Nc + c0;
+            const double *src = p.Uc + (ptrdiff_t)min(max(rq + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
             const bool ok0 = row_ok && c0 < p.Nc, ok1 = row_ok && c0 + 1 < p.Nc;
-            cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.Uc, ok0);
-            cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.Uc, ok1);
+            cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
+            cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
             if (lane == 0) {
                 const int rr = row_ok ? r : 0;
                 cp_async16(warp_ring + off + 1536, p.row_w + rr, row_ok);
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
     if (IN == IN_PROLONG && active) {
         const int rq_first = __shfl_sync(0xffffffffu, tab, 0);
         // lower coarse row of the first cell: the only one that is not staged
-        const double *c_lo = p.Uc + (ptrdiff_t)(rq_first - p.uc_row0) * p.Nc;
+        const double *c_lo = p.Uc + (ptrdiff_t)rq_first * p.Nc;
         if (col_ok) {
             const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
             top.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
@@ -387,14 +389,14 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
 
             // refill the slot with row r + DEPTH (the values above are in registers by now)
             if (FAST) {
-                if (IN != IN_ZERO) cp_async16(ring_base + slot_off, Up + (ptrdiff_t)(r + STREAM_DEPTH - row0) * ldn + cx);
-                if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1 - row0) * ldn + cx);
+                if (IN != IN_ZERO) cp_async16(ring_base + slot_off, Up + (ptrdiff_t)(r + STREAM_DEPTH) * ldn + cx);
+                if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
                 if (IN == IN_PROLONG) {
                     const int c0 = cbase + 2 * lane;
-                    const double *src = p.Uc + (ptrdiff_t)min(max(cell_of_row(r + STREAM_DEPTH) + 1 - p.uc_row0, 0), p.uc_rows - 1) * p.Nc + c0;
+                    const double *src = p.Uc + (ptrdiff_t)min(max(cell_of_row(r + STREAM_DEPTH) + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
                     const bool ok0 = c0 < p.Nc, ok1 = c0 + 1 < p.Nc;
-                    cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.Uc, ok0);
-                    cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.Uc, ok1);
+                    cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
+                    cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
                     if (lane == 0) {
                         cp_async16(warp_ring + slot_off + 1536, p.row_w + r + STREAM_DEPTH, true);
                         cp_async4(warp_ring + slot_off + 1552, p.row_cell + r + STREAM_DEPTH, true);
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
             // ---- x is now level S, row r-S
             {
                 const int i = r - S;
-                if (Op && i >= own_r_lo && i < own_r_hi && col_own) *reinterpret_cast<double2 *>(Op + (ptrdiff_t)(i - row0) * ldn + cx) = x;
+                if (Op && i >= own_r_lo && i < own_r_hi && col_own) *reinterpret_cast<double2 *>(Op + (ptrdiff_t)i * ldn + cx) = x;
             }
 
             if (NEED_R) {
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
                         const double cw = ri.y;
                         const double np = shfl_dn1(d_prev.x), nc = shfl_dn1(d_cur.x);
                         const bool row_edge = crow == 0 || crow == p.M - 1;
-                        double *out = p.Fc + (ptrdiff_t)(crow - p.fc_row0) * p.M;
+                        double *out = p.Fc + (ptrdiff_t)crow * p.M;
                         if (ccx >= 0) out[ccx] = (row_edge || zx) ? 0.0 : restrict_at(d_prev.x, d_prev.y, d_cur.x, d_cur.y, ax, cw);
                         if (ccy >= 0) out[ccy] = (row_edge || zy) ? 0.0 : restrict_at(d_prev.y, np, d_cur.y, nc, ay, cw);
                     }
@@ -476,8 +478,8 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamPar
 
     for (int rb = r_first; rb <= r_last; rb += U) {
         // interior rows only, and every row the chunk loads (up to DEPTH ahead) is present locally
-        const bool fast = strip_fast && rb - NLV >= 1 && rb + U + STREAM_DEPTH <= N - 1 && rb - 1 >= row0 &&
-                          rb + U + STREAM_DEPTH < row_end;
+        const bool fast = strip_fast && rb - NLV >= 1 && rb + U + STREAM_DEPTH <= N - 1 && rb - 1 >= p.row0 &&
+                          rb + U + STREAM_DEPTH < p.row0 + p.rows;
         if (fast) chunk(BoolTag<true>(), rb);
         else chunk(BoolTag<false>(), rb);
     }
