@@ -144,6 +144,10 @@ int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double
  * (one per rank) with halo exchange per fused pass; smaller levels are agglomerated on rank 0.
  * Rendezvous: rank 0 calls mgDistUniqueId, the host program broadcasts the 128 bytes (e.g. with
  * torch.distributed), every rank calls mgDistInit.  NCCL is bound with dlopen at run time. */
+/* Host-only planning of the slab geometry for a ladder of level sizes: per level
+ * [N, distributed?, bound[0..world]] (world+3 ints).  Needs no GPU.  Returns the number of
+ * levels, or < 0 if a distributed level cannot be served (odd size / non-fusable pair). */
+int mgDistPlan(const int *ladder, int n_levels, int world, int threshold, int *out, int max_out);
 int mgDistUniqueId(void *out128);
 int mgDistInit(int rank, int world, const void *id128);
 void mgDistShutdown(void);

@@ -8,7 +8,7 @@ argument meaning as the reference (MG_solver_CPU.cpp:16-34), grids resident on t
 There is no CPU fallback: importing works anywhere, but every operator needs the built
 library and a CUDA device and raises loudly otherwise.
 """
-from .api import (run_cycle_dist_emulated, run_cycle_dist, dist_init,  # noqa: F401
+from .api import (run_cycle_dist_emulated, run_cycle_dist, dist_init, dist_plan,  # noqa: F401
                   MGLibraryError, DeviceGrid, GpuOps, init, lib, lib_path, run_cycle, run_cycle_host,  # noqa: F401
                   RUN_FUSED, RUN_UNFUSED, RUN_QUIET, RUN_SKIP_SOURCE, RUN_NO_FINAL_ERROR)
 from . import cycles  # noqa: F401

@@ -63,6 +63,7 @@ ABI = {
     "mgRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),
+    "mgDistPlan": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgDistUniqueId": (C.c_int, [_vp]),
     "mgDistInit": (C.c_int, [C.c_int, C.c_int, _vp]),
     "mgDistShutdown": (None, []),
@@ -346,3 +347,19 @@ def run_cycle_dist(path, threshold, flags=RUN_FUSED | RUN_QUIET, want_U=False, m
     if want_U:
         out["U_own"] = U[: (hi.value - lo.value) * N].copy()
     return out
+
+
+def dist_plan(ladder, world, threshold):
+    """Slab geometry of every level of `ladder` (host-only): list of dict(N, dist, bounds)."""
+    l = lib()
+    n = len(ladder)
+    arr = (C.c_int * n)(*ladder)
+    out = (C.c_int * (n * (world + 3)))()
+    rc = l.mgDistPlan(arr, n, world, threshold, out, len(out))
+    if rc < 0:
+        raise MGLibraryError("mgDistPlan failed with code %d" % rc)
+    plan = []
+    for i in range(n):
+        o = out[i * (world + 3):(i + 1) * (world + 3)]
+        plan.append(dict(N=o[0], dist=bool(o[1]), bounds=list(o[2:])))
+    return plan

@@ -139,12 +139,77 @@ public:
 };
 std::unique_ptr<NcclComm> g_nccl_comm;
 
-// ------------------------------------------------------------------ geometry
+// ------------------------------------------------------------------ geometry (host only, no device state)
+// fine row whose pair (f, f+1) produces coarse row c: the floor map of doRestriction
+// (MG_solver_CPU.cpp:661-662), with the two coarse boundary rows pinned to 0 and N-2 as in
+// mg_fused.cu.  Empty vector = the map is not injective / leaves the grid (pair not fusable).
+std::vector<int> fine_of_coarse_host(int N, int M)
+{
+    std::vector<int> out;
+    if (!(M >= 3 && M < N && N >= 4)) return out;
+    const double h_f = 1.0 / (double)(N - 1), h_c = 1.0 / (double)(M - 1);
+    out.assign((size_t)M, 0);
+    int prev = 0;
+    for (int c = 1; c <= M - 2; ++c) {
+        const int f = (int)floor((double)c * h_c / h_f);
+        if (f < 1 || f > N - 3 || f <= prev) return std::vector<int>();
+        out[c] = prev = f;
+    }
+    if (prev >= N - 2) return std::vector<int>();
+    out[M - 1] = N - 2;
+    return out;
+}
+
+bool pair_fusable_host(int N, int M)
+{
+    return N >= 4 && N % 2 == 0 && M >= 3 && (double)(N - 1) >= 1.2 * (double)(M - 1) && !fine_of_coarse_host(N, M).empty();
+}
+
 struct LevelGeom {
     int N = 0;
     bool dist = false;
     std::vector<int> bound;   // dist: owned rows of rank k = [bound[k], bound[k+1])
 };
+
+// rank k owns the coarse rows whose lower fine row it owns
+std::vector<int> coarse_bounds(const LevelGeom &fine, int M, int world)
+{
+    const std::vector<int> foc = fine_of_coarse_host(fine.N, M);
+    std::vector<int> b((size_t)world + 1, M);
+    int c = 0;
+    for (int k = 0; k < world; ++k) {
+        while (c < M && foc[c] < fine.bound[k]) ++c;
+        b[k] = c;
+    }
+    return b;
+}
+
+LevelGeom top_geometry(int N, int world, int threshold)
+{
+    LevelGeom g;
+    g.N = N;
+    g.dist = world > 1 && N >= threshold && N % 2 == 0 && N / world >= 2 * HALO;
+    if (g.dist)
+        for (int k = 0; k <= world; ++k) g.bound.push_back((int)((long long)N * k / world));
+    return g;
+}
+
+// coarse geometry induced by the fine one; false (+why) if a distributed fine level cannot be served
+bool induce_geometry(const LevelGeom &fine, int M, int world, int threshold, LevelGeom &coarse, std::string &why)
+{
+    coarse.N = M;
+    coarse.dist = false;
+    coarse.bound.clear();
+    if (!fine.dist) return true;
+    if (!pair_fusable_host(fine.N, M)) { why = "a distributed level needs an even size and a fusable transfer pair"; return false; }
+    if (!(world > 1 && M >= threshold)) return true;
+    const std::vector<int> b = coarse_bounds(fine, M, world);
+    for (int k = 0; k < world; ++k)
+        if (b[k + 1] - b[k] < 2 * HALO) return true;   // slabs too thin for single-neighbour halos: agglomerate
+    coarse.dist = true;
+    coarse.bound = b;
+    return true;
+}
 
 Slab slab_of(const LevelGeom &g, int rank)
 {
@@ -230,20 +295,7 @@ public:
     // coarse geometry induced by the fine one (see the header comment)
     bool induce(const LevelGeom &fine, int M, LevelGeom &coarse, std::string &why)
     {
-        coarse.N = M;
-        coarse.dist = false;
-        coarse.bound.clear();
-        if (!fine.dist) return true;
-        if (!slab_pair_fusable(fine.N, M)) { why = "a distributed level needs an even size and a fusable transfer pair"; return false; }
-        if (!want_dist(M)) return true;
-        std::vector<int> b(comm.world + 1);
-        for (int k = 0; k < comm.world; ++k) b[k] = restrict_first_coarse_at_or_after(fine.N, M, fine.bound[k]);
-        b[comm.world] = M;
-        for (int k = 0; k < comm.world; ++k)
-            if (b[k + 1] - b[k] < 2 * HALO) return true;   // slabs too thin for single-neighbour halos: agglomerate
-        coarse.dist = true;
-        coarse.bound = b;
-        return true;
+        return induce_geometry(fine, M, comm.world, threshold_, coarse, why);
     }
 
     // ---- halo exchange of one array of level `li` (which: 0 U, 1 F)
@@ -317,11 +369,7 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     DistCycle cy(comm, threshold);
     Context &c = ctx();
     {
-        LevelGeom g;
-        g.N = N_max;
-        g.dist = cy.want_dist(N_max) && N_max % 2 == 0 && N_max / comm.world >= 2 * HALO;
-        if (g.dist)
-            for (int k = 0; k <= comm.world; ++k) g.bound.push_back((int)((long long)N_max * k / comm.world));
+        const LevelGeom g = top_geometry(N_max, comm.world, threshold);
         // one-rank-per-process runs may keep the top-level source slab between calls
         const bool cacheable = (flags & MG_RUN_SKIP_SOURCE) && cy.ranks.size() == 1;
         double *borrowed = nullptr;
@@ -445,9 +493,7 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             // ---- distributed fine level
             // F_c target per rank: the coarse slab's F if the coarse level is distributed, else a
             // temporary holding exactly the rank's coarse rows (rank 0 writes into the full array)
-            std::vector<int> cb(comm.world + 1);
-            for (int k = 0; k < comm.world; ++k) cb[k] = restrict_first_coarse_at_or_after(fine.N, next_N, fine.bound[k]);
-            cb[comm.world] = next_N;
+            const std::vector<int> cb = coarse_bounds(fine, next_N, comm.world);
             std::vector<double *> fc_tmp(cy.ranks.size(), nullptr);
             std::vector<Slab> fc_slab(cy.ranks.size());
             for (size_t i = 0; i < cy.ranks.size(); ++i) {
@@ -600,9 +646,7 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
                 cy.exchange(lc, 0);
                 for (size_t i = 0; i < cy.ranks.size(); ++i) uc_slab[i] = cy.ranks[i].lv[lc].slab;
             } else {
-                std::vector<int> cb(comm.world + 1);
-                for (int k = 0; k < comm.world; ++k) cb[k] = restrict_first_coarse_at_or_after(fine.N, coarse.N, fine.bound[k]);
-                cb[comm.world] = coarse.N;
+                const std::vector<int> cb = coarse_bounds(fine, coarse.N, comm.world);
                 std::vector<Xfer> xs;
                 const double *full = nullptr;
                 for (auto &st : cy.ranks) if (st.rank == 0) full = st.lv[lc].U;
@@ -743,6 +787,28 @@ int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags,
     return run_dist(comm, path, threshold, flags, recs, max_recs, res, U_host, nullptr, nullptr, nullptr);
 }
 
+int mgDistPlan(const int *ladder, int n_levels, int world, int threshold, int *out, int max_out)
+{
+    // out: per level [N, dist, bound[0..world]] = world + 3 ints; pure host computation (no GPU needed)
+    if (n_levels < 1 || world < 1) return -1;
+    const int stride = world + 3;
+    if (max_out < n_levels * stride) return -2;
+    LevelGeom g = top_geometry(ladder[0], world, threshold);
+    for (int l = 0; l < n_levels; ++l) {
+        if (l > 0) {
+            LevelGeom c;
+            std::string why;
+            if (!induce_geometry(g, ladder[l], world, threshold, c, why)) return -(10 + l);
+            g = c;
+        }
+        int *o = out + (size_t)l * stride;
+        o[0] = g.N;
+        o[1] = g.dist ? 1 : 0;
+        for (int k = 0; k <= world; ++k) o[2 + k] = g.dist ? g.bound[k] : (k == 0 ? 0 : g.N);
+    }
+    return n_levels;
+}
+
 int mgDistUniqueId(void *out128)
 {
     if (!g_nccl.load()) return 1;
@@ -771,12 +837,7 @@ int mgDistInit(int rank, int world, const void *id128)
 int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, int *own_hi)
 {
     if (!g_nccl_comm) { fail(-34, "mgDistSourceSlab: call mgDistInit first"); return 12; }
-    LevelGeom g;
-    g.N = N;
-    const int world = g_nccl_comm->world;
-    g.dist = world > 1 && N >= threshold && N % 2 == 0 && N / world >= 2 * HALO;
-    if (g.dist)
-        for (int k = 0; k <= world; ++k) g.bound.push_back((int)((long long)N * k / world));
+    const LevelGeom g = top_geometry(N, g_nccl_comm->world, threshold);
     const Slab s = slab_of(g, g_nccl_comm->rank);
     const bool present = g.dist || g_nccl_comm->rank == 0;
     *row0 = s.row0; *rows = present ? s.rows : 0; *own_lo = s.own_lo; *own_hi = present ? s.own_hi : s.own_lo;
