@@ -38,8 +38,9 @@ def build(force=False, verbose=False):
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    if force or _newer(LIB, deps):
-        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-ccbin", "g++", "-ldl"]
+    extra = os.environ.get("MG_NVCC_EXTRA", "").split()      # tuning experiments, e.g. -DMG_STREAM_WARPS=4
+    if force or extra or _newer(LIB, deps):
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-shared", "-o", LIB] + srcs + ["-ccbin", "g++", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

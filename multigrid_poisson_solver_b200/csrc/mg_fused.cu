@@ -77,7 +77,8 @@ void launch_stream(StreamParams &p)
     // Rows per task: about four tasks per resident warp when the grid is large enough (halo rows
     // cost (2S+3)/H of extra work, so at least 32 rows), otherwise as many tasks as 16-row
     // segments allow.
-    const int resident_warps = 2 * c.sm_count * STREAM_WARPS;
+    constexpr int STREAM_WARPS = stream_shape(RES).warps, STREAM_MIN_CTAS = stream_shape(RES).min_ctas;
+    const int resident_warps = STREAM_MIN_CTAS * c.sm_count * STREAM_WARPS;
     const int own_rows = p.own_hi - p.own_lo;
     int H = g_force_H;
     if (H <= 0) {
@@ -98,16 +99,16 @@ void launch_stream(StreamParams &p)
     if (p.Uout) p.Uout -= fine_shift;
     if (p.Fc) p.Fc -= (ptrdiff_t)p.fc_row0 * p.M;
     if (p.Uc) p.Uc -= (ptrdiff_t)p.uc_row0 * p.Nc;
-    const int blocks = std::max(1, std::min(2 * c.sm_count, (p.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS));
+    const int blocks = std::max(1, std::min(STREAM_MIN_CTAS * c.sm_count, (p.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS));
     if (ERR) p.partials = partials_buf((size_t)p.n_tasks);
     p.counter = c.counters + 8;   // [8] queue head, [9] finished warps (self-resetting)
     static bool opted_in = false;   // one flag per instantiation
     if (!opted_in) {
-        check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem_bytes(IN)),
+        check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem_bytes(IN, STREAM_WARPS)),
               "cudaFuncSetAttribute(k_stream)");
         opted_in = true;
     }
-    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, stream_smem_bytes(IN), c.stream>>>(p);
+    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, stream_smem_bytes(IN, STREAM_WARPS), c.stream>>>(p);
     c.launches++;
     check(cudaGetLastError(), "k_stream");
 }

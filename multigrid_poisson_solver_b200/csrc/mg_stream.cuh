@@ -36,15 +36,37 @@ namespace mg {
 
 enum { IN_LOAD = 0, IN_ZERO = 1, IN_PROLONG = 2 };
 
-constexpr int STREAM_WARPS = 8;         // warps (= strips) per CTA
+#ifndef MG_STREAM_DEPTH
+#define MG_STREAM_DEPTH 4
+#endif
+// CTA shape per variant (measured on B200, N = 16384): passes without restriction run best as
+// 4-warp CTAs, three per SM (12 warps, up to 168 registers, no spills); the -1 node (RES) as
+// 8-warp CTAs, two per SM (16 warps, 128 registers).
+#ifndef MG_RES_WARPS
+#define MG_RES_WARPS 8
+#endif
+#ifndef MG_RES_CTAS
+#define MG_RES_CTAS 2
+#endif
+#ifndef MG_PLAIN_WARPS
+#define MG_PLAIN_WARPS 4
+#endif
+#ifndef MG_PLAIN_CTAS
+#define MG_PLAIN_CTAS 3
+#endif
+struct StreamShape { int warps, min_ctas; };
+__host__ __device__ constexpr StreamShape stream_shape(bool res)
+{
+    return res ? StreamShape{MG_RES_WARPS, MG_RES_CTAS} : StreamShape{MG_PLAIN_WARPS, MG_PLAIN_CTAS};
+}
 constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
-constexpr int STREAM_DEPTH = 8;         // rows in flight per warp (cp.async ring in shared memory), power of two
+constexpr int STREAM_DEPTH = MG_STREAM_DEPTH;   // rows in flight per warp (cp.async ring in shared memory), power of two
 // shared memory: [warp][slot][U | F (| coarse row, 1 node only)][lane] x 16 B
 // the 1 node adds the staged coarse row (512 B) and the row's {row_w, row_cell} entry (32 B)
 __host__ __device__ constexpr int stream_slot_bytes(int in) { return in == 2 ? 3 * 512 + 32 : 2 * 512; }
-__host__ __device__ constexpr int stream_smem_bytes(int in)
+__host__ __device__ constexpr int stream_smem_bytes(int in, int warps)
 {
-    return STREAM_WARPS * (STREAM_DEPTH * stream_slot_bytes(in) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
+    return warps * (STREAM_DEPTH * stream_slot_bytes(in) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
 }
 
 struct StreamParams {
@@ -133,15 +155,16 @@ __device__ __forceinline__ double residual_fast(double u, double s4, double f, d
 
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 
-// 16-byte asynchronous global->shared copy (LDGSTS); !valid zero-fills the destination.
+// 16-byte asynchronous global->shared copy (LDGSTS, L2 only: streamed rows must not evict the
+// few local-memory lines from L1); !valid zero-fills the destination.
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gsrc, bool valid)
 {
     const int src_bytes = valid ? 16 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gsrc)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 // 8-byte variant (coarse rows of odd length are only 8-byte aligned)
 __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void *gsrc, bool valid)
@@ -186,8 +209,9 @@ template <bool B>
 struct BoolTag { static constexpr bool value = B; };
 
 template <int S, int IN, bool ERR, bool RES>
-__global__ void __launch_bounds__(STREAM_WARPS * 32, 2) k_stream(const StreamParams p)
+__global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES).min_ctas) k_stream(const StreamParams p)
 {
+    constexpr int STREAM_WARPS = stream_shape(RES).warps;
     constexpr bool NEED_R = ERR || RES;
     using G = StreamGeo<S, NEED_R, RES>;
     constexpr int NLV = S + (NEED_R ? 1 : 0);    // levels that keep a two-row window (level t feeds stage t)
