@@ -369,6 +369,47 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         }
         prev_rq = rq_first - 1;                   // so that the first step shifts `top` down and loads the upper row
     }
+    // Level 0 of the 1 node, U_f + P(U_c) (MG_solver_CPU.cpp:700 + :569), for the fine row staged in
+    // ring slot `so`.  Branch-free so that the compiler can interleave it with the sweeps of the
+    // previous row; lanes whose quotient left the safe range of the FMA division report `bad`.
+    double2 x_next = make_double2(0.0, 0.0);
+    double pvx = 0.0, pvy = 0.0, puf_x = 0.0, puf_y = 0.0;   // operands kept for the rare IEEE redo
+    auto prolong_from_slot = [&](unsigned so) -> bool {
+        const double2 uf = lds2(ring_base + so);
+        const double2 wr = lds2(warp_ring + so + 1536);          // row_w[r]
+        const int rq = lds_int(warp_ring + so + 1552);           // row_cell[r]
+        const bool changed = rq != prev_rq;                      // the cell moved up one coarse row
+        const unsigned cs = warp_ring + so + 1024;
+        const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
+        double2 ntop;
+        ntop.x = __dadd_rn(__dmul_rn(lds1(cs + ox), wcx.x), __dmul_rn(lds1(cs + ox + 8), wcx.y));
+        ntop.y = __dadd_rn(__dmul_rn(lds1(cs + oy), wcy.x), __dmul_rn(lds1(cs + oy + 8), wcy.y));
+        bot.x = changed ? top.x : bot.x;
+        bot.y = changed ? top.y : bot.y;
+        top.x = changed ? ntop.x : top.x;
+        top.y = changed ? ntop.y : top.y;
+        prev_rq = rq;
+        const double vx = __dadd_rn(__dmul_rn(bot.x, wr.x), __dmul_rn(top.x, wr.y));
+        const double vy = __dadd_rn(__dmul_rn(bot.y, wr.x), __dmul_rn(top.y, wr.y));
+        const double d = p.c_dx, y = p.inv_c_dx;
+        const double qx = div_fast(vx, d, y), qy = div_fast(vy, d, y);
+        x_next.x = __dadd_rn(uf.x, div_fast(qx, d, y));
+        x_next.y = __dadd_rn(uf.y, div_fast(qy, d, y));
+        pvx = vx; pvy = vy; puf_x = uf.x; puf_y = uf.y;
+        return div_unsafe(vx) | div_unsafe(qx) | div_unsafe(vy) | div_unsafe(qy);
+    };
+    auto prolong_redo = [&](bool bad) {                          // rare: IEEE divisions for the whole warp
+        if (__any_sync(0xffffffffu, bad)) {
+            const double d = p.c_dx;
+            x_next.x = __dadd_rn(puf_x, __ddiv_rn(__ddiv_rn(pvx, d), d));
+            x_next.y = __dadd_rn(puf_y, __ddiv_rn(__ddiv_rn(pvy, d), d));
+        }
+    };
+    if (IN == IN_PROLONG) {
+        cp_async_wait<STREAM_DEPTH - 1>();        // the group of row r_first has landed
+        __syncwarp();
+        prolong_redo(prolong_from_slot(0));
+    }
 
     // One chunk = U consecutive steps.  FAST: every row touched by every stage is an interior
     // row, every column of the window is an interior column and all loads are in range, so the
@@ -378,37 +419,21 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
 #pragma unroll
         for (int k = 0; k < U; ++k) {
             const int r = rb + k;
-            cp_async_wait<STREAM_DEPTH - 1>();                    // the group of row r has landed
+            bool bad = false;
             double2 x = make_double2(0.0, 0.0), f_new = x;
-            if (IN != IN_ZERO) x = lds2(ring_base + slot_off);
-            if (NF > 0) f_new = lds2(ring_base + slot_off + 512);
-
-            // ---- level 0 of the 1 node: U_f + P(U_c)   (MG_solver_CPU.cpp:700 + :569)
             if (IN == IN_PROLONG) {
-                __syncwarp();                                     // the slot was filled by all lanes (and lane 0's table entry)
-                const double2 wr = lds2(warp_ring + slot_off + 1536);   // row_w[r]
-                const int rq = lds_int(warp_ring + slot_off + 1552);    // row_cell[r]
-                if ((FAST || r <= N - 1) && rq != prev_rq) {      // the cell moved up one coarse row
-                    const unsigned cs = warp_ring + slot_off + 1024;
-                    bot = top;
-                    const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
-                    top.x = __dadd_rn(__dmul_rn(lds1(cs + ox), wcx.x), __dmul_rn(lds1(cs + ox + 8), wcx.y));
-                    top.y = __dadd_rn(__dmul_rn(lds1(cs + oy), wcy.x), __dmul_rn(lds1(cs + oy + 8), wcy.y));
-                    prev_rq = rq;
-                }
-                const double vx = __dadd_rn(__dmul_rn(bot.x, wr.x), __dmul_rn(top.x, wr.y));
-                const double vy = __dadd_rn(__dmul_rn(bot.y, wr.x), __dmul_rn(top.y, wr.y));
-                const double d = p.c_dx, y = p.inv_c_dx;
-                const double qx = div_fast(vx, d, y), qy = div_fast(vy, d, y);
-                double px = div_fast(qx, d, y), py = div_fast(qy, d, y);
-                const bool bad = div_unsafe(vx) | div_unsafe(qx) | div_unsafe(vy) | div_unsafe(qy);
-                if (__any_sync(0xffffffffu, bad)) {               // rare: redo with IEEE divisions
-                    px = __ddiv_rn(__ddiv_rn(vx, d), d);
-                    py = __ddiv_rn(__ddiv_rn(vy, d), d);
-                }
-                x.x = __dadd_rn(x.x, px);
-                x.y = __dadd_rn(x.y, py);
-                __syncwarp();                                     // every lane is done with the staged row
+                // level 0 of row r was produced one step ago; produce row r+1 now, next to this row's sweeps
+                cp_async_wait<STREAM_DEPTH - 2>();                // the groups of rows r and r+1 have landed
+                __syncwarp();                                     // slots are filled by all lanes (and lane 0's table entry)
+                x = x_next;
+                if (NF > 0) f_new = lds2(ring_base + slot_off + 512);
+                unsigned slot_n = slot_off + SLOT_BYTES;
+                if (slot_n == STREAM_DEPTH * SLOT_BYTES) slot_n = 0;
+                bad = prolong_from_slot(slot_n);
+            } else {
+                cp_async_wait<STREAM_DEPTH - 1>();                // the group of row r has landed
+                if (IN != IN_ZERO) x = lds2(ring_base + slot_off);
+                if (NF > 0) f_new = lds2(ring_base + slot_off + 512);
             }
 
             // refill the slot with row r + DEPTH (the values above are in registers by now)
@@ -497,6 +522,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                     d_prev = d_cur;
                 }
             }
+            if (IN == IN_PROLONG) prolong_redo(bad);
         }
     };
 
