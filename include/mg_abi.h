@@ -103,6 +103,18 @@ void mgExactSolve(int N, double L, double *U, double *F, double target_error, in
 double *mgUpLeg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, double *F, int step,
                 double *error_slot);
 
+/* The coarse tail of a cycle in one kernel: a node sub-stream that starts at a level of at most
+ * mgCoarseTailMaxN() points per side and returns to it (parallel arrays, one entry per node:
+ * kind -1/0/1, step (-1 = error trigger), zero_init, the size the node works on, next_N for -1
+ * nodes, target/option for 0 nodes).  All levels live in shared memory.  out_slots (from
+ * mgScalarSlot) receives per node {smoothing error, sweeps or GS iterations}.  Returns 0 if it
+ * ran, > 0 if the stream is not representable (caller falls back to one call per node). */
+int mgCoarseTailMaxN(void);
+int mgCoarseTailMaxOps(void);
+int mgCoarseTail(double L, double *U_entry, double *F_entry, int n_ops, const int *kind, const int *step,
+                 const int *zero_init, const int *N_of_op, const int *next_N, const double *target, const int *option,
+                 double *out_slots);
+
 /* ---------------------------------------------------------------- the driver
  * Cycle.txt interpreter = the reference's main() loop (MG_solver_CPU.cpp:36-462)
  * over a device-resident level stack (linkedlist.cpp). */

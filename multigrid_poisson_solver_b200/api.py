@@ -60,6 +60,9 @@ ABI = {
     "mgDownLeg": (_vp, [C.c_int, C.c_double, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _dp]),
     "mgExactSolve": (None, [C.c_int, C.c_double, _vp, _vp, C.c_double, C.c_int, _dp]),
     "mgUpLeg": (_vp, [C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, C.c_int, _dp]),
+    "mgCoarseTailMaxN": (C.c_int, []),
+    "mgCoarseTailMaxOps": (C.c_int, []),
+    "mgCoarseTail": (C.c_int, [C.c_double, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp]),
     "mgRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),

@@ -52,6 +52,58 @@ __device__ __forceinline__ double prolong_at(double c1, double c2, double c3, do
     return __ddiv_rn(__ddiv_rn(v, c_dx), c_dx);
 }
 
+// ---- 1-D transfer maps (shared by the table kernels and the coarse-tail kernel)
+// doRestriction's map of coarse index t (MG_solver_CPU.cpp:661-664): lower fine index and weight.
+__device__ __forceinline__ void restrict_table_entry(int t, int N, int M, int &lo, double &w)
+{
+    const double h_f = __ddiv_rn(1.0, (double)(N - 1)), h_c = __ddiv_rn(1.0, (double)(M - 1));
+    const double pos = __dmul_rn((double)t, h_c);
+    lo = (int)floor(__ddiv_rn(pos, h_f));
+    w = __ddiv_rn(fmod(pos, h_f), h_f);
+}
+
+// doProlongation in gather form (MG_solver_CPU.cpp:688-718): the coarse cell q
+// that owns fine index t is the one with ceil(q*ratio) <= t < ceil((q+1)*ratio), or -1.
+__device__ __forceinline__ int prolong_cell_of(int t, int N, double ratio)
+{
+    int q = (int)floor(__ddiv_rn((double)t, ratio));
+    q = max(0, min(q, N - 2));
+    while (q > 0 && ceil(__dmul_rn((double)q, ratio)) > (double)t) --q;
+    while (q < N - 2 && ceil(__dmul_rn((double)(q + 1), ratio)) <= (double)t) ++q;
+    const bool inside = ceil(__dmul_rn((double)q, ratio)) <= (double)t && (double)t < ceil(__dmul_rn((double)(q + 1), ratio));
+    return inside ? q : -1;
+}
+
+// Row and column entry of fine index t (N coarse, M fine): cell and weights {c_hi - f, f - c_lo}.
+// Rows and columns differ only in the patched last line (:701-718).
+__device__ __forceinline__ void prolong_table_entry(int t, int N, int M, int &row_cell, int &col_cell, double2 &row_w,
+                                                    double2 &col_w)
+{
+    const double c_dx = __ddiv_rn(1.0, (double)(N - 1)), f_dx = __ddiv_rn(1.0, (double)(M - 1));
+    const double ratio = __ddiv_rn(c_dx, f_dx);
+    int rq, cq;
+    double rf, cf;
+    if (t < M - 1) {
+        rq = cq = prolong_cell_of(t, N, ratio);
+        if (rq < 0) rq = cq = max(0, min((int)floor(__ddiv_rn((double)t, ratio)), N - 2));  // never written by the reference
+        rf = cf = __dmul_rn((double)t, f_dx);
+    } else {
+        int q1 = prolong_cell_of(M - 2, N, ratio);
+        if (q1 < 0) q1 = N - 2;
+        const int q2 = prolong_cell_of(M - 1, N, ratio);
+        const double f_last = __dmul_rn((double)(M - 1), f_dx);
+        rq = (q2 >= 0 && q2 != q1) ? q2 : q1;  // :706-718 (the patch ends the row loop of its own cell only)
+        rf = f_last;
+        if (q2 >= 0) { cq = q2; cf = f_last; }  // regular pass rewrites the patched column (last writer wins)
+        else         { cq = q1; cf = 1.0; }     // :701-704
+    }
+    const double r_lo = __dmul_rn((double)rq, c_dx), c_lo = __dmul_rn((double)cq, c_dx);
+    row_cell = rq;
+    col_cell = cq;
+    row_w = make_double2(__dsub_rn(__dadd_rn(r_lo, c_dx), rf), __dsub_rn(rf, r_lo));
+    col_w = make_double2(__dsub_rn(__dadd_rn(c_lo, c_dx), cf), __dsub_rn(cf, c_lo));
+}
+
 // Deterministic CTA-wide sum (fixed shuffle tree, fixed warp order).  Result valid in thread 0.
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double *smem32)

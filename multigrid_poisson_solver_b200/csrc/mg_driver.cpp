@@ -38,7 +38,7 @@ struct Level {
 struct Pending {  // a trace record whose scalar lives in a pinned slot until the next sync
     int rec;
     int slot;
-    bool is_iters;
+    bool is_iters;   // the slot holds a sweep / iteration count (-> steps) instead of an error
 };
 
 class Cycle {
@@ -132,6 +132,96 @@ public:
         printf("              Error = %lf\n", l.smoothing_error);
     }
 
+    // Collects the node sub-stream that stays at or below the current (small) level and runs it
+    // as one kernel.  Returns the number of nodes consumed (0 = not applicable, < 0 = error).
+    int try_tail(const std::vector<double> &tok, size_t &cur, size_t &pos, const std::vector<int> &ladder, int con_step,
+                 int con_N, double L, bool quiet)
+    {
+        std::vector<int> kind, step, zero, Nop, nextN, option;
+        std::vector<double> target;
+        std::vector<int> sizes{top().N};                  // simulated stack below the entry level
+        size_t c = cur, p = pos;
+        int sim_init = init_;
+        const size_t base_depth = stack_.size();
+        const int max_ops = mgCoarseTailMaxOps();
+        for (;;) {
+            if (c >= tok.size()) break;
+            const int node = (int)tok[c];
+            if (node == 2) break;
+            if (node == 1 && sizes.size() == 1) break;    // would prolong above the entry level
+            if ((int)kind.size() >= max_ops) return 0;
+            ++c;
+            if (node == -1) {
+                int st, nn;
+                if (con_step == 0) { if (c >= tok.size()) return 0; st = (int)tok[c++]; } else st = con_step;
+                if (con_N == 0) { if (c >= tok.size()) return 0; nn = (int)tok[c++]; }
+                else { if (p + 1 >= ladder.size()) return 0; nn = ladder[++p]; }
+                if (st == 0) return 0;                    // FMG placeholder: leave it to the node-by-node path
+                const bool restart = sim_init == 0 && base_depth + sizes.size() - 1 == 1;
+                kind.push_back(-1); step.push_back(st); zero.push_back(restart ? 0 : 1); Nop.push_back(sizes.back());
+                nextN.push_back(nn); option.push_back(0); target.push_back(0.0);
+                sizes.push_back(nn);
+            } else if (node == 0) {
+                if (c + 2 > tok.size()) return 0;
+                const double tg = tok[c++];
+                const int opt = (int)tok[c++];
+                kind.push_back(0); step.push_back(0); zero.push_back(0); Nop.push_back(sizes.back());
+                nextN.push_back(0); option.push_back(opt); target.push_back(tg);
+            } else if (node == 1) {
+                int st;
+                if (con_step == 0) { if (c >= tok.size()) return 0; st = (int)tok[c++]; } else st = con_step;
+                if (con_N != 0 && p > 0) --p;
+                sizes.pop_back();
+                if (base_depth + sizes.size() - 1 == 1) sim_init = 0;
+                kind.push_back(1); step.push_back(st); zero.push_back(0); Nop.push_back(sizes.back());
+                nextN.push_back(0); option.push_back(0); target.push_back(0.0);
+            } else return 0;
+        }
+        if (sizes.size() != 1 || kind.size() < 2) return 0;
+        const int n = (int)kind.size();
+        if (slot_ + 2 * n > MG_SCALAR_SLOTS - 1) harvest();
+        const int slot0 = slot_;
+        Level &l = top();
+        const int rc = mgCoarseTail(L, l.U, l.F, n, kind.data(), step.data(), zero.data(), Nop.data(), nextN.data(), target.data(),
+                                    option.data(), mgScalarSlot(slot0));
+        if (rc == 10) return -10;
+        if (rc != 0) return 0;                           // not representable: node-by-node
+        slot_ += 2 * n;
+        const int first_rec = n_recs_;
+        for (int i = 0; i < n; ++i) {
+            const int r = record(kind[i], Nop[i], kind[i] == 0 ? -1 : step[i], 0.0);
+            if (kind[i] == 0) defer(r, slot0 + 2 * i + 1, true);
+            else {
+                if (step[i] != 0) defer(r, slot0 + 2 * i, false);
+                if (step[i] < 0) defer(r, slot0 + 2 * i + 1, true);
+            }
+        }
+        init_ = sim_init;
+        if (!quiet) {                                    // the log needs the values now
+            harvest();
+            for (int i = 0; i < n; ++i) {
+                const mgTraceRec *t = (recs_ && first_rec + i < max_recs_) ? &recs_[first_rec + i] : nullptr;
+                if (kind[i] == 0) {
+                    printf("          ~Exact Solver~\nCurrent Grid Size N = %d\n", Nop[i]);
+                    if (option[i] == 1) printf("   Use Exact Solver = GaussSeidel Even / Odd\n");
+                    printf("       Target Error = %.3e\n", target[i]);
+                    continue;
+                }
+                if (kind[i] == 1) fputs("             *\n             |\nProlongation |\n             |\n             *\n", stdout);
+                if (step[i] != 0) {
+                    const double e = t ? t->err : *mgScalarSlot(slot0 + 2 * i);
+                    const int st = t ? t->steps : (int)*mgScalarSlot(slot0 + 2 * i + 1);
+                    printf("          ~Smoothing~\nCurrent Grid Size N = %d\n    Smoothing Steps = %d\n              Error = %lf\n", Nop[i], st, e);
+                }
+                if (kind[i] == -1) fputs("             *\n             |\n Restriction |\n             |\n             *\n", stdout);
+            }
+        }
+        const int consumed = (int)(c - cur);
+        cur = c;
+        pos = p;
+        return consumed > 0 ? consumed : 0;
+    }
+
     int flags_;
     mgTraceRec *recs_;
     int max_recs_;
@@ -153,12 +243,19 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
         fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path);
         return 1;
     }
+    // The whole file as whitespace-delimited numeric tokens (what `ifstream >>` sees), so that the
+    // interpreter can look ahead for a coarse tail.
+    std::vector<double> tok;
+    for (double d; f >> d;) tok.push_back(d);
+    size_t cur = 0;
+    auto have = [&](size_t n) { return cur + n <= tok.size(); };
+    auto next_int = [&]() { return (int)tok[cur++]; };
+    if (!have(7)) return 2;
     double L, min_x, min_y;
     int con_step, con_N, N_max, N_min;
-    f >> L >> min_x >> min_y;   // :103
-    f >> con_step >> con_N;     // :106
-    f >> N_max >> N_min;        // :109
-    if (!f) return 2;
+    L = tok[cur++]; min_x = tok[cur++]; min_y = tok[cur++];   // :103
+    con_step = next_int(); con_N = next_int();                // :106
+    N_max = next_int(); N_min = next_int();                   // :109
 
     std::vector<int> ladder;    // :111-146
     if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
@@ -188,14 +285,22 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
 
     int rc = 0;
     int node = 0;
-    while (f >> node) {                                               // :158-160 (stops at EOF instead of re-running)
+    const int tail_max_N = (fused && !getenv("MG_NO_TAIL")) ? mgCoarseTailMaxN() : 0;
+    while (have(1)) {                                                 // :158-160 (stops at EOF instead of re-running)
+        // ---- coarse tail: the whole sub-cycle below a small level in one kernel (mg_tail.cu)
+        if (tail_max_N && cy.top().N <= tail_max_N && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
+            const int took = cy.try_tail(tok, cur, pos, ladder, con_step, con_N, L, quiet);
+            if (took < 0) { rc = -took; break; }
+            if (took > 0) continue;
+        }
+        node = next_int();
         if (node == 2) break;                                         // :162
         if (mgLastErrorCode()) { rc = 10; break; }
 
         if (node == -1) {                                             // :169-301
             int step, next_N;
-            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
-            if (con_N == 0) { if (!(f >> next_N)) { rc = 3; break; } }
+            if (con_step == 0) { if (!have(1)) { rc = 3; break; } step = next_int(); } else step = con_step;
+            if (con_N == 0) { if (!have(1)) { rc = 3; break; } next_N = next_int(); }
             else {
                 if (pos + 1 >= ladder.size()) { rc = 4; break; }
                 next_N = ladder[++pos];
@@ -242,7 +347,9 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             if (!quiet) fputs(kRestrictArt, stdout);
         } else if (node == 0) {                                       // :305-325
             double target; int option;
-            if (!(f >> target >> option)) { rc = 3; break; }
+            if (!have(2)) { rc = 3; break; }
+            target = tok[cur++];
+            option = next_int();
             Level &l = cy.top();
             const int slot = cy.next_slot();
             mgExactSolve(l.N, L, l.U, l.F, target, option, mgScalarSlot(slot));
@@ -257,7 +364,7 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             }
         } else if (node == 1) {                                       // :329-424
             int step;
-            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
+            if (con_step == 0) { if (!have(1)) { rc = 3; break; } step = next_int(); } else step = con_step;
             if (con_N != 0 && pos > 0) --pos;
             if (cy.depth() < 2) { rc = 5; break; }                    // reference: null prevNode
             Level coarse = cy.top();
