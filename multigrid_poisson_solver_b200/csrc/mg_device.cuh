@@ -104,6 +104,71 @@ __device__ __forceinline__ void prolong_table_entry(int t, int N, int M, int &ro
     col_w = make_double2(__dsub_rn(__dadd_rn(c_lo, c_dx), cf), __dsub_rn(cf, c_lo));
 }
 
+// Red/black Gauss-Seidel (MG_solver_CPU.cpp:952-1066) on a grid held in shared memory, run by the
+// first `warps` warps of a CTA (all of their threads must call; other warps must not).  u must be
+// zero on entry (:993).  Three named barriers per iteration, convergence test every iteration as
+// in the reference; the mean |residual| is folded in a fixed order (warp tree, then warp order).
+// Returns the iteration count (same value in every calling thread).
+__device__ __forceinline__ void named_barrier(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int MAX_PTS>   // points per thread: N*N <= MAX_PTS * 32 * warps
+__device__ int gauss_seidel_shared(int N, double h2, double inv_h2, double target, double *u, const double *f, double *partials,
+                                   int warps, int bar_id, int max_iters)
+{
+    const int T = warps * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = N * N;
+    int cell[MAX_PTS];
+    unsigned red_mask = 0, in_mask = 0;
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        const int c = tid + k * T;
+        cell[k] = c < n ? c : 0;
+        const int i = cell[k] / N, j = cell[k] - i * N;
+        if (c < n && i > 0 && i < N - 1 && j > 0 && j < N - 1) {
+            in_mask |= 1u << k;
+            if (((i + j) & 1) == 0) red_mask |= 1u << k;   // the ieven table (:972-980) enumerates (ix+iy) even
+        }
+    }
+    const double denom = (double)((N - 2) * (N - 2));
+    int it = 0;
+    double e;
+    do {
+#pragma unroll
+        for (int colour = 0; colour < 2; ++colour) {
+            const unsigned m = colour == 0 ? red_mask : (in_mask & ~red_mask);
+#pragma unroll
+            for (int k = 0; k < MAX_PTS; ++k)
+                if (m >> k & 1u) {
+                    const int c = cell[k];
+                    u[c] = gauss_seidel_at(u[c - 1], u[c + 1], u[c + N], u[c - N], __dmul_rn(h2, f[c]));
+                }
+            if (warps == 1) __syncwarp(); else named_barrier(bar_id, T);
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k)
+            if (in_mask >> k & 1u) {
+                const int c = cell[k];
+                acc = __dadd_rn(acc, fabs(residual_at(u[c], sum4(u[c + N], u[c - N], u[c + 1], u[c - 1]), f[c], inv_h2)));
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+        if (warps > 1) {
+            // double-buffered by iteration parity: no barrier is needed before the next write
+            double *slot = partials + (it & 1) * 32;
+            if (lane == 0) slot[warp] = acc;
+            named_barrier(bar_id, T);
+            acc = 0.0;
+            for (int w = 0; w < warps; ++w) acc = __dadd_rn(acc, slot[w]);
+        }
+        e = __ddiv_rn(acc, denom);                                    // :1059
+        ++it;
+    } while (e > target && it < max_iters);
+    return it;
+}
+
 // Deterministic CTA-wide sum (fixed shuffle tree, fixed warp order).  Result valid in thread 0.
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double *smem32)

@@ -24,64 +24,23 @@ namespace {
 constexpr int GS_MAX_ITERS = 200 * 1000 * 1000;
 
 // ---------------------------------------------------------------- GS, whole grid in shared memory
-// One CTA.  Each thread owns up to PTS interior points (index and colour precomputed), so
-// the iteration body has no integer division.  5 CTA barriers per iteration.
-template <int THREADS, int PTS>
-__global__ void __launch_bounds__(THREADS) k_gs_smem(int N, double h2, double inv_h2, double target, double *__restrict__ U,
-                                                     const double *__restrict__ F, int *__restrict__ iters_out,
-                                                     double *iters_slot)
+// One CTA of `warps` warps (mg_device.cuh: gauss_seidel_shared): three named barriers per
+// iteration, each thread owns up to PTS interior points.
+template <int PTS>
+__global__ void __launch_bounds__(1024) k_gs_smem(int N, int warps, double h2, double inv_h2, double target, double *__restrict__ U,
+                          const double *__restrict__ F, int *__restrict__ iters_out, double *iters_slot)
 {
     extern __shared__ double sm[];
-    const int n = N * N;
-    double *u = sm, *f = sm + n, *red = sm + 2 * n;  // red[0..31] tree scratch, red[32] broadcast
-    for (int k = threadIdx.x; k < n; k += THREADS) {
+    const int n = N * N, T = warps * 32;
+    double *u = sm, *f = sm + n, *partials = sm + 2 * n;
+    for (int k = threadIdx.x; k < n; k += T) {
         u[k] = 0.0;  // :993
         f[k] = F[k];
     }
-    const int nin = N - 2, npts = nin * nin;
-    int cell[PTS];
-    bool is_red[PTS];
-#pragma unroll
-    for (int k = 0; k < PTS; ++k) {
-        const int p = threadIdx.x + k * THREADS;
-        cell[k] = -1;
-        is_red[k] = false;
-        if (p < npts) {
-            const int ix = 1 + p % nin, iy = 1 + p / nin;
-            cell[k] = ix + iy * N;
-            is_red[k] = ((ix + iy) & 1) == 0;  // the ieven table (:972-980) enumerates (ix+iy) even
-        }
-    }
     __syncthreads();
-
-    const double denom = (double)((N - 2) * (N - 2));
-    double err;
-    int it = 0;
-    do {
-#pragma unroll
-        for (int colour = 0; colour < 2; ++colour) {
-#pragma unroll
-            for (int k = 0; k < PTS; ++k) {
-                const int c = cell[k];
-                if (c >= 0 && is_red[k] == (colour == 0))
-                    u[c] = gauss_seidel_at(u[c - 1], u[c + 1], u[c + N], u[c - N], __dmul_rn(h2, f[c]));
-            }
-            __syncthreads();
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < PTS; ++k) {
-            const int c = cell[k];
-            if (c >= 0) acc = __dadd_rn(acc, fabs(residual_at(u[c], sum4(u[c + N], u[c - N], u[c + 1], u[c - 1]), f[c], inv_h2)));
-        }
-        const double total = block_sum<THREADS>(acc, red);
-        if (threadIdx.x == 0) red[32] = __ddiv_rn(total, denom);  // :1059
-        __syncthreads();
-        err = red[32];
-        ++it;
-    } while (err > target && it < GS_MAX_ITERS);
-
-    for (int k = threadIdx.x; k < n; k += THREADS) U[k] = u[k];
+    const int it = gauss_seidel_shared<PTS>(N, h2, inv_h2, target, u, f, partials, warps, 1, GS_MAX_ITERS);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += T) U[k] = u[k];
     if (threadIdx.x == 0) {
         *iters_out = it;
         if (iters_slot) { *iters_slot = (double)it; __threadfence_system(); }
@@ -231,24 +190,23 @@ void launch_gauss_seidel(int N, double L, double *U, const double *F, double tar
 {
     const Spacing sp = spacing(N, L);
     Context &c = ctx();
-    const size_t smem = ((size_t)2 * N * N + 33) * sizeof(double);
-    const int npts = (N - 2) * (N - 2);
+    const size_t smem = ((size_t)2 * N * N + 64) * sizeof(double);
+    const int n = N * N;
     if (N >= 3 && smem <= 220 * 1024) {
-#define GS_CASE(THREADS, PTS)                                                                                   \
+        // as few warps as keep <= 4 (16 for the largest grids) points per thread: barriers dominate an iteration
+        const int warps = n <= 128 ? 1 : n <= 512 ? 4 : n <= 1024 ? 8 : n <= 4096 ? 32 : 32;
+#define GS_CASE(PTS)                                                                                            \
     do {                                                                                                        \
         static size_t opted = 0;                                                                                \
         if (smem > opted) {                                                                                     \
-            check(cudaFuncSetAttribute(k_gs_smem<THREADS, PTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                       (int)smem), "cudaFuncSetAttribute");                                     \
+            check(cudaFuncSetAttribute(k_gs_smem<PTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                  "cudaFuncSetAttribute");                                                                      \
             opted = smem;                                                                                       \
         }                                                                                                       \
-        MG_LAUNCH((k_gs_smem<THREADS, PTS>), 1, THREADS, smem, N, sp.h2, sp.inv_h2, target, U, F, c.gs_iters, iters_slot); \
+        MG_LAUNCH((k_gs_smem<PTS>), 1, warps * 32, smem, N, warps, sp.h2, sp.inv_h2, target, U, F, c.gs_iters, iters_slot); \
     } while (0)
-        if (npts <= 64) GS_CASE(64, 1);
-        else if (npts <= 256) GS_CASE(256, 1);
-        else if (npts <= 1024) GS_CASE(1024, 1);
-        else if (npts <= 4096) GS_CASE(1024, 4);
-        else GS_CASE(1024, 16);
+        if (n <= 4096) GS_CASE(4);
+        else GS_CASE(16);
 #undef GS_CASE
         return;
     }

@@ -133,56 +133,12 @@ __device__ int tail_smooth(int N, int step, double h2, double inv_h2, double *u,
     return done;
 }
 
-// GaussSeidel (:952-1066) on a grid small enough for ONE warp (N*N <= 128): warp-level barriers
-// only; the other warps wait at the CTA barrier after it.
-__device__ int tail_gs_one_warp(int N, double h2, double inv_h2, double target, double *u, const double *f)
-{
-    const int lane = threadIdx.x, n = N * N;
-    int idx[4];
-    bool in[4], red_pt[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = lane + 32 * k;
-        idx[k] = c < n ? c : 0;
-        const int i = idx[k] / N, j = idx[k] - i * N;
-        in[k] = c < n && interior(i, j, N);
-        red_pt[k] = ((i + j) & 1) == 0;
-    }
-    const double denom = (double)((N - 2) * (N - 2));
-    int it = 0;
-    double e;
-    do {
-#pragma unroll
-        for (int colour = 0; colour < 2; ++colour) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (in[k] && red_pt[k] == (colour == 0)) {
-                    const int c = idx[k];
-                    u[c] = gauss_seidel_at(u[c - 1], u[c + 1], u[c + N], u[c - N], __dmul_rn(h2, f[c]));
-                }
-            __syncwarp();
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (in[k]) {
-                const int c = idx[k];
-                acc = __dadd_rn(acc, fabs(residual_at(u[c], sum4(u[c + N], u[c - N], u[c + 1], u[c - 1]), f[c], inv_h2)));
-            }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
-        e = __ddiv_rn(acc, denom);          // xor butterfly: every lane holds the same bits
-        ++it;
-    } while (e > target && it < 100000000);
-    return it;
-}
-
 __global__ void __launch_bounds__(TAIL_THREADS, 1) k_coarse_tail(const TailProgram P)
 {
     extern __shared__ double sm[];
     double *red = sm + P.off_tab;            // [0..32] reduction scratch
-    int *itab = (int *)(red + 40);           // 2 x 64 ints
-    double *dtab = red + 40 + 64;            // 6 x 64 doubles
+    int *itab = (int *)(red + 112);          // 2 x 64 ints   (red[48..111]: Gauss-Seidel warp partials)
+    double *dtab = red + 112 + 64;           // 6 x 64 doubles
     double *scratch = sm + P.off_scratch;
     const int tid = threadIdx.x;
 
@@ -231,33 +187,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_coarse_tail(const TailProgr
             // GaussSeidel                                                     :952-1066
             TAIL_FOR_POINTS(N) u[i * N + j] = 0.0;
             __syncthreads();
-            if (N * N <= 128) {
-                if (tid < 32) done = tail_gs_one_warp(N, op.h2, op.inv_h2, op.target, u, f);
-                __syncthreads();
-            } else {
-                const double denom = (double)((N - 2) * (N - 2));
-                double e;
-                do {
-                    for (int colour = 0; colour < 2; ++colour) {
-                        TAIL_FOR_POINTS(N) {
-                            const int c = i * N + j;
-                            if (interior(i, j, N) && ((i + j) & 1) == colour)
-                                u[c] = gauss_seidel_at(u[c - 1], u[c + 1], u[c + N], u[c - N], __dmul_rn(op.h2, f[c]));
-                        }
-                        __syncthreads();
-                    }
-                    double acc = 0.0;
-                    TAIL_FOR_POINTS(N) {
-                        const int c = i * N + j;
-                        if (interior(i, j, N))
-                            acc = __dadd_rn(acc, fabs(residual_at(u[c], sum4(u[c + N], u[c - N], u[c + 1], u[c - 1]), f[c], op.inv_h2)));
-                    }
-                    double s = tail_block_sum(acc, red);
-                    if (tid == 0) s = __ddiv_rn(s, denom);
-                    e = tail_bcast(s, red);
-                    ++done;
-                } while (e > op.target && done < 100000000);
-            }
+            // few warps with named barriers: a 1024-thread barrier costs more than a whole iteration
+            const int warps = N * N <= 128 ? 1 : N * N <= 512 ? 4 : N * N <= 1024 ? 8 : 32;   // <= 4 points per thread
+            if (tid < warps * 32) done = gauss_seidel_shared<4>(N, op.h2, op.inv_h2, op.target, u, f, red + 48, warps, 1, 100000000);
+            __syncthreads();
         } else {
             // 1 node: U_f += doProlongation(U_c), then smoothing                :350-416
             const int Nc = P.N[op.lev + 1];
@@ -347,7 +280,7 @@ extern "C" int mgCoarseTail(double L, double *U_entry, double *F_entry, int n_op
     }
     P.off_scratch = off; off += P.N[0] * P.N[0];
     off = (off + 1) & ~1;                          // 16-byte alignment of the double2 tables
-    P.off_tab = off; off += 40 + 64 + 6 * 64;
+    P.off_tab = off; off += 112 + 64 + 6 * 64;
     const size_t smem = (size_t)off * sizeof(double);
     if (smem > 200 * 1024) return 8;
     P.U_entry = U_entry;
