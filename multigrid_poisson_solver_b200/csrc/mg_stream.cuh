@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
             } else {
                 issue(r + STREAM_DEPTH, slot_off, IN == IN_PROLONG ? cell_of_row(r + STREAM_DEPTH) : 0);
             }
+
             slot_off += SLOT_BYTES;
             if (slot_off == STREAM_DEPTH * SLOT_BYTES) slot_off = 0;
 
@@ -502,7 +503,8 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 if (ERR) {
                     // red = (row + column) even: exactly one of the lane's two columns (:609-611)
                     const double v = (rho & 1) ? res.y : res.x;   // cx is even
-                    if (rho >= own_r_lo && rho < own_r_hi && col_own) err_acc = __dadd_rn(err_acc, fabs(v));
+                    const bool take = col_own && rho >= own_r_lo && rho < own_r_hi;
+                    err_acc = __dadd_rn(err_acc, take ? fabs(v) : 0.0);   // + 0.0 is exact
                 }
                 if (RES) {
                     const double2 d_cur = make_double2(-res.x, -res.y);   // D = -D (:277-280)
