@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgb200.so")
 EXE = os.path.join(HERE, "MG_GPU")
 SOURCES = ["mg_abi.cu", "mg_kernels.cu", "mg_fused.cu", "mg_exact.cu", "mg_dist.cu", "mg_tail.cu", "mg_driver.cpp"]
-HEADERS = ["mg_context.h", "mg_kernels.h", "mg_fused.h", "mg_device.cuh", "mg_stream.cuh", os.path.join("..", "..", "include", "mg_abi.h")]
+HEADERS = ["mg_context.h", "mg_kernels.h", "mg_fused.h", "mg_device.cuh", "mg_stream.cuh", "mg_stream4.cuh", os.path.join("..", "..", "include", "mg_abi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -10,6 +10,7 @@
 
 #include "mg_kernels.h"
 #include "mg_stream.cuh"
+#include "mg_stream4.cuh"
 
 namespace mg {
 namespace {
@@ -67,18 +68,19 @@ const FusedRestrictTable &fused_restrict_table(int N, int M)
     return g_restrict_tables.emplace(std::make_pair(N, M), t).first->second;
 }
 
-template <int S, int IN, bool ERR, bool RES>
-void launch_stream(StreamParams &p)
+int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
+
+// Task geometry, persistent grid and launch shared by the two streaming kernels.
+template <typename Kernel>
+void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int min_ctas, int smem_bytes, bool err, bool &opted_in)
 {
-    using G = StreamGeo<S, ERR || RES, RES>;
     Context &c = ctx();
     const int N = p.N;
-    p.n_strips = (N + G::W - 1) / G::W;
+    p.n_strips = (N + W - 1) / W;
     // Rows per task: about four tasks per resident warp when the grid is large enough (halo rows
     // cost (2S+3)/H of extra work, so at least 32 rows), otherwise as many tasks as 16-row
     // segments allow.
-    constexpr int STREAM_WARPS = stream_shape(RES).warps, STREAM_MIN_CTAS = stream_shape(RES).min_ctas;
-    const int resident_warps = STREAM_MIN_CTAS * c.sm_count * STREAM_WARPS;
+    const int resident_warps = min_ctas * c.sm_count * warps;
     const int own_rows = p.own_hi - p.own_lo;
     int H = g_force_H;
     if (H <= 0) {
@@ -99,18 +101,35 @@ void launch_stream(StreamParams &p)
     if (p.Uout) p.Uout -= fine_shift;
     if (p.Fc) p.Fc -= (ptrdiff_t)p.fc_row0 * p.M;
     if (p.Uc) p.Uc -= (ptrdiff_t)p.uc_row0 * p.Nc;
-    const int blocks = std::max(1, std::min(STREAM_MIN_CTAS * c.sm_count, (p.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS));
-    if (ERR) p.partials = partials_buf((size_t)p.n_tasks);
+    const int blocks = std::max(1, std::min(min_ctas * c.sm_count, (p.n_tasks + warps - 1) / warps));
+    if (err) p.partials = partials_buf((size_t)p.n_tasks);
     p.counter = c.counters + 8;   // [8] queue head, [9] finished warps (self-resetting)
-    static bool opted_in = false;   // one flag per instantiation
     if (!opted_in) {
-        check(cudaFuncSetAttribute(k_stream<S, IN, ERR, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem_bytes(IN, STREAM_WARPS)),
-              "cudaFuncSetAttribute(k_stream)");
+        check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(k_stream)");
         opted_in = true;
     }
-    k_stream<S, IN, ERR, RES><<<blocks, STREAM_WARPS * 32, stream_smem_bytes(IN, STREAM_WARPS), c.stream>>>(p);
+    kernel<<<blocks, warps * 32, smem_bytes, c.stream>>>(p);
     c.launches++;
     check(cudaGetLastError(), "k_stream");
+}
+
+template <int S, int IN, bool ERR, bool RES>
+void launch_stream(StreamParams &p)
+{
+    // Measured on B200 (N = 16384): 4 columns per lane win for the passes without restriction (smoothing
+    // pass 1.05 vs 1.09 ms); with restriction the 230-254 registers leave 8 warps per SM and lose (1.40 vs 1.22 ms).
+    if (IN != IN_PROLONG && !RES && g_cols4) {
+        // instantiated only for IN_LOAD / IN_ZERO (the branch is dead for IN_PROLONG)
+        constexpr int IN4 = IN == IN_PROLONG ? IN_LOAD : IN;
+        using G4 = Stream4Geo<S, ERR || RES, RES>;
+        static bool opted4 = false;
+        launch_stream_kernel(k_stream4<S, IN4, ERR, RES>, p, G4::W, S4_WARPS, S4_MIN_CTAS, stream4_smem_bytes(), ERR, opted4);
+        return;
+    }
+    using G = StreamGeo<S, ERR || RES, RES>;
+    constexpr int STREAM_WARPS = stream_shape(RES).warps, STREAM_MIN_CTAS = stream_shape(RES).min_ctas;
+    static bool opted_in = false;   // one flag per instantiation
+    launch_stream_kernel(k_stream<S, IN, ERR, RES>, p, G::W, STREAM_WARPS, STREAM_MIN_CTAS, stream_smem_bytes(IN, STREAM_WARPS), ERR, opted_in);
 }
 
 template <int IN, bool ERR, bool RES>
@@ -305,6 +324,7 @@ void fused_init()
 {
     if (const char *h = getenv("MG_STREAM_H")) g_force_H = atoi(h);
     if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
+    if (const char *d = getenv("MG_COLS4")) g_cols4 = atoi(d);
 }
 
 int smooth_pass_count(int N, int step)
