@@ -146,6 +146,14 @@ typedef struct mgCycleResult {
 int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_top,
                    mgTraceRec *recs, int max_recs, mgCycleResult *res);
 
+/* The same interpreter on ONE level owned by the caller: runs the node sub-stream that starts at
+ * tok[*cur] (tok = the cycle file as numeric tokens) and returns to that level; stops before the
+ * 1 node that would prolong above it, before the code 2, or at the end.  Used by the slab driver
+ * for the levels agglomerated on rank 0 (execute == 0: parse only, keeps the other ranks in step). */
+int mgRunSubcycle(const double *tok, int n_tok, int *cur, int *pos, const int *ladder, int n_ladder, int con_step,
+                  int con_N, double L, int N, double **U, double **W, double *F, int depth_offset, int *init_io,
+                  int flags, mgTraceRec *recs, int max_recs, int *n_recs_io, int execute);
+
 /* Same with HOST buffers: F_host (N_max^2, may be NULL -> getSource on device) is
  * copied to the device, the cycle runs, the solution is copied back into U_host. */
 int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double *U_host,

@@ -356,10 +356,16 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
 {
     std::ifstream f(path);
     if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
+    std::vector<double> tok;
+    for (double d; f >> d;) tok.push_back(d);
+    if (tok.size() < 7) return 2;
+    size_t cur = 0;
+    auto have = [&](size_t n) { return cur + n <= tok.size(); };
+    auto next_int = [&]() { return (int)tok[cur++]; };
     double L, min_x, min_y;
     int con_step, con_N, N_max, N_min;
-    f >> L >> min_x >> min_y >> con_step >> con_N >> N_max >> N_min;
-    if (!f) return 2;
+    L = tok[cur++]; min_x = tok[cur++]; min_y = tok[cur++];
+    con_step = next_int(); con_N = next_int(); N_max = next_int(); N_min = next_int();
     std::vector<int> ladder;
     if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
     if (con_N == 2) for (int n = N_max; n >= N_min; --n) ladder.push_back(n);
@@ -437,13 +443,35 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
 
     int rc = 0, node = 0;
     std::string why;
-    while (f >> node) {
+    while (have(1)) {
+        // ---- agglomerated sub-cycle: everything that happens at or below a level held by rank 0
+        // alone is run by the single-GPU interpreter (fused nodes + coarse tail kernel) on rank 0;
+        // the other ranks parse the same nodes without executing them.
+        if (!cy.geom.back().dist && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
+            harvest();                                   // the sub-interpreter uses the scalar-slot ring too
+            const int li = (int)cy.geom.size() - 1;
+            int icur = (int)cur, ipos = (int)pos, n_rec_io = n_recs, init_io = cy.init_;
+            int sub_rc = 0;
+            for (auto &st : cy.ranks) {
+                RankLevel &l = st.lv[li];
+                int c2 = (int)cur, p2 = (int)pos, r2 = n_recs, i2 = cy.init_;
+                sub_rc = mgRunSubcycle(tok.data(), (int)tok.size(), &c2, &p2, ladder.data(), (int)ladder.size(), con_step, con_N, L,
+                                       cy.geom[li].N, &l.U, &l.W, l.F, li, &i2, flags,
+                                       (st.rank == 0 || !comm.is_local(0)) ? recs : nullptr, max_recs, &r2, st.rank == 0 ? 1 : 0);
+                icur = c2; ipos = p2; n_rec_io = r2; init_io = i2;
+                if (sub_rc) break;
+            }
+            if (sub_rc) { rc = sub_rc; break; }
+            cur = (size_t)icur; pos = (size_t)ipos; n_recs = n_rec_io; cy.init_ = init_io;
+            continue;
+        }
+        node = next_int();
         if (node == 2) break;
         if (c.err_code) { rc = 10; break; }
         if (node == -1) {
             int step, next_N;
-            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
-            if (con_N == 0) { if (!(f >> next_N)) { rc = 3; break; } }
+            if (con_step == 0) { if (!have(1)) { rc = 3; break; } step = next_int(); } else step = con_step;
+            if (con_N == 0) { if (!have(1)) { rc = 3; break; } next_N = next_int(); }
             else { if (pos + 1 >= ladder.size()) { rc = 4; break; } next_N = ladder[++pos]; }
             if (step == 0) continue;
             const int li = (int)cy.geom.size() - 1;
@@ -578,7 +606,9 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             if (!quiet) fputs(kRestrictArt, stdout);
         } else if (node == 0) {
             double target; int option;
-            if (!(f >> target >> option)) { rc = 3; break; }
+            if (!have(2)) { rc = 3; break; }
+            target = tok[cur++];
+            option = next_int();
             const int li = (int)cy.geom.size() - 1;
             if (cy.geom[li].dist) { fail(-41, "the exact solver runs on an agglomerated level: lower the coarsest size or raise the threshold"); rc = 21; break; }
             const int rr = record(0, cy.geom[li].N, -1, 0.0);
@@ -600,7 +630,7 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             }
         } else if (node == 1) {
             int step;
-            if (con_step == 0) { if (!(f >> step)) { rc = 3; break; } } else step = con_step;
+            if (con_step == 0) { if (!have(1)) { rc = 3; break; } step = next_int(); } else step = con_step;
             if (con_N != 0 && pos > 0) --pos;
             if (cy.geom.size() < 2) { rc = 5; break; }
             const int lc = (int)cy.geom.size() - 1, lf = lc - 1;

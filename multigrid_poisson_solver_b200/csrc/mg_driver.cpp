@@ -33,6 +33,7 @@ struct Level {
     int step = 0;
     double smoothing_error = 0;
     bool owns_F = true;      // false when F is the caller's top-level source used in place
+    bool borrowed = false;   // the whole level belongs to the caller (mgRunSubcycle)
 };
 
 struct Pending {  // a trace record whose scalar lives in a pinned slot until the next sync
@@ -53,6 +54,7 @@ public:
     {
         Level l;
         l.N = N;
+        if (dry_) { stack_.push_back(l); return; }     // parse-only run: sizes are all that is tracked
         l.U = mgGridAlloc(N);
         l.F = borrowed_F ? borrowed_F : mgGridAlloc(N);
         l.owns_F = borrowed_F == nullptr;
@@ -63,14 +65,16 @@ public:
     void pop()  // linkedlist.cpp:46-69
     {
         Level &l = stack_.back();
-        mgGridFree(l.U); mgGridFree(l.W); mgGridFree(l.D);
-        if (l.owns_F) mgGridFree(l.F);
+        if (!dry_ && !l.borrowed) {
+            mgGridFree(l.U); mgGridFree(l.W); mgGridFree(l.D);
+            if (l.owns_F) mgGridFree(l.F);
+        }
         stack_.pop_back();
-        if (stack_.size() == 1) init_ = 0;
+        if (stack_.size() + depth_offset_ == 1) init_ = 0;
     }
     Level &top() { return stack_.back(); }
     size_t depth() const { return stack_.size(); }
-    bool restart_top() const { return init_ == 0 && stack_.size() == 1; }  // :209, :252
+    bool restart_top() const { return init_ == 0 && stack_.size() + depth_offset_ == 1; }  // :209, :252
 
     int next_slot()
     {
@@ -142,7 +146,7 @@ public:
         std::vector<int> sizes{top().N};                  // simulated stack below the entry level
         size_t c = cur, p = pos;
         int sim_init = init_;
-        const size_t base_depth = stack_.size();
+        const size_t base_depth = stack_.size() + depth_offset_;
         const int max_ops = mgCoarseTailMaxOps();
         for (;;) {
             if (c >= tok.size()) break;
@@ -177,7 +181,7 @@ public:
                 nextN.push_back(0); option.push_back(0); target.push_back(0.0);
             } else return 0;
         }
-        if (sizes.size() != 1 || kind.size() < 2) return 0;
+        if (sizes.size() != 1 || kind.size() < 2 || dry_) return 0;
         const int n = (int)kind.size();
         if (slot_ + 2 * n > MG_SCALAR_SLOTS - 1) harvest();
         const int slot0 = slot_;
@@ -222,6 +226,8 @@ public:
         return consumed > 0 ? consumed : 0;
     }
 
+    bool dry_ = false;            // parse only (ranks that do not hold an agglomerated sub-cycle)
+    size_t depth_offset_ = 0;     // levels of the caller's stack above stack_[0] (mgRunSubcycle)
     int flags_;
     mgTraceRec *recs_;
     int max_recs_;
@@ -235,57 +241,34 @@ public:
 const char *kRestrictArt = "             *\n             |\n Restriction |\n             |\n             *\n";
 const char *kProlongArt = "             *\n             |\nProlongation |\n             |\n             *\n";
 
-int run(const char *path, int flags, const double *F_top, double *U_top, mgTraceRec *recs, int max_recs,
-        mgCycleResult *res)
+struct NodeStream {           // the token stream after the three header lines, with the ladder position
+    const std::vector<double> &tok;
+    size_t cur, pos;
+    const std::vector<int> &ladder;
+    int con_step, con_N;
+    double L;
+};
+
+// The node loop of main() (MG_solver_CPU.cpp:158-426).  stop_depth == 0: until the code 2 / end
+// of the stream.  stop_depth > 0 (sub-cycle of a larger driver): also stops, without reading the
+// node, when a 1 node would pop the stack below stop_depth levels or when the code 2 comes up.
+int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
 {
-    std::ifstream f(path);
-    if (!f.is_open()) {
-        fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path);
-        return 1;
-    }
-    // The whole file as whitespace-delimited numeric tokens (what `ifstream >>` sees), so that the
-    // interpreter can look ahead for a coarse tail.
-    std::vector<double> tok;
-    for (double d; f >> d;) tok.push_back(d);
-    size_t cur = 0;
-    auto have = [&](size_t n) { return cur + n <= tok.size(); };
-    auto next_int = [&]() { return (int)tok[cur++]; };
-    if (!have(7)) return 2;
-    double L, min_x, min_y;
-    int con_step, con_N, N_max, N_min;
-    L = tok[cur++]; min_x = tok[cur++]; min_y = tok[cur++];   // :103
-    con_step = next_int(); con_N = next_int();                // :106
-    N_max = next_int(); N_min = next_int();                   // :109
-
-    std::vector<int> ladder;    // :111-146
-    if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
-    if (con_N == 2) for (int n = N_max; n >= N_min; --n) ladder.push_back(n);
-    size_t pos = 0;
-
-    Cycle cy(flags, recs, max_recs);
-    const bool fused = cy.fused(), quiet = cy.quiet();
-    // In fused mode the log needs each node's error, which costs a sync per node; quiet runs stay asynchronous.
-    const bool sync_each_node = fused && !quiet;
-
-    if ((flags & MG_RUN_SKIP_SOURCE) && F_top) {
-        cy.push(N_max, const_cast<double *>(F_top));                  // the operators never write F
-    } else {
-        cy.push(N_max);                                               // :149
-        getSource(N_max, L, cy.top().F, min_x, min_y);                // :153 (outside the timer)
-    }
-    mgSync();
-
-    cudaStream_t stream = (cudaStream_t)mgStream();
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    const int launches0 = mgKernelLaunches();
-    const auto wall0 = std::chrono::steady_clock::now();
-    cudaEventRecord(ev0, stream);                                     // :156
-
     int rc = 0;
     int node = 0;
-    const int tail_max_N = (fused && !getenv("MG_NO_TAIL")) ? mgCoarseTailMaxN() : 0;
+    const bool fused = cy.fused(), quiet = cy.quiet(), dry = cy.dry_;
+    const bool sync_each_node = fused && !quiet;
+    const std::vector<double> &tok = s.tok;
+    size_t &cur = s.cur, &pos = s.pos;
+    const std::vector<int> &ladder = s.ladder;
+    const int con_step = s.con_step, con_N = s.con_N;
+    const double L = s.L;
+    mgTraceRec *recs = cy.recs_;
+    const int max_recs = cy.max_recs_;
+    (void)recs; (void)max_recs;
+    auto have = [&](size_t n) { return cur + n <= tok.size(); };
+    auto next_int = [&]() { return (int)tok[cur++]; };
+    const int tail_max_N = (fused && !dry && !getenv("MG_NO_TAIL")) ? mgCoarseTailMaxN() : 0;
     while (have(1)) {                                                 // :158-160 (stops at EOF instead of re-running)
         // ---- coarse tail: the whole sub-cycle below a small level in one kernel (mg_tail.cu)
         if (tail_max_N && cy.top().N <= tail_max_N && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
@@ -293,6 +276,8 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             if (took < 0) { rc = -took; break; }
             if (took > 0) continue;
         }
+        if (stop_depth > 0 && (int)tok[cur] == 1 && cy.depth() <= stop_depth) break;   // would prolong above the sub-cycle
+        if (stop_depth > 0 && (int)tok[cur] == 2) break;             // the caller consumes the end marker
         node = next_int();
         if (node == 2) break;                                         // :162
         if (mgLastErrorCode()) { rc = 10; break; }
@@ -310,6 +295,11 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             const bool zero_init = !cy.restart_top();                 // :209-214 / :252-257
             const int fine_N = l->N;
 
+            if (dry) {                                                // parse only: same stack moves, same record count
+                cy.record(-1, fine_N, step > 0 ? step : 0, 0.0);
+                cy.push(next_N);
+                continue;
+            }
             if (fused && step > 0) {
                 const int slot = cy.next_slot();
                 cy.push(next_N);
@@ -351,6 +341,7 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             target = tok[cur++];
             option = next_int();
             Level &l = cy.top();
+            if (dry) { cy.record(0, l.N, -1, 0.0); continue; }
             const int slot = cy.next_slot();
             mgExactSolve(l.N, L, l.U, l.F, target, option, mgScalarSlot(slot));
             const int r = cy.record(0, l.N, -1, 0.0);
@@ -369,6 +360,11 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             if (cy.depth() < 2) { rc = 5; break; }                    // reference: null prevNode
             Level coarse = cy.top();
             Level *l = &cy.stack_[cy.depth() - 2];
+            if (dry) {
+                cy.pop();
+                cy.record(1, cy.top().N, step > 0 ? step : 0, 0.0);
+                continue;
+            }
 
             if (fused) {
                 const int slot = step > 0 ? cy.next_slot() : -1;
@@ -407,6 +403,57 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
             break;
         }
     }
+    return rc;
+}
+
+int run(const char *path, int flags, const double *F_top, double *U_top, mgTraceRec *recs, int max_recs,
+        mgCycleResult *res)
+{
+    std::ifstream f(path);
+    if (!f.is_open()) {
+        fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path);
+        return 1;
+    }
+    // The whole file as whitespace-delimited numeric tokens (what `ifstream >>` sees), so that the
+    // interpreter can look ahead for a coarse tail.
+    std::vector<double> tok;
+    for (double d; f >> d;) tok.push_back(d);
+    size_t cur = 0;
+    auto have = [&](size_t n) { return cur + n <= tok.size(); };
+    auto next_int = [&]() { return (int)tok[cur++]; };
+    if (!have(7)) return 2;
+    double L, min_x, min_y;
+    int con_step, con_N, N_max, N_min;
+    L = tok[cur++]; min_x = tok[cur++]; min_y = tok[cur++];   // :103
+    con_step = next_int(); con_N = next_int();                // :106
+    N_max = next_int(); N_min = next_int();                   // :109
+
+    std::vector<int> ladder;    // :111-146
+    if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
+    if (con_N == 2) for (int n = N_max; n >= N_min; --n) ladder.push_back(n);
+    size_t pos = 0;
+
+    Cycle cy(flags, recs, max_recs);
+    const bool quiet = cy.quiet();
+
+    if ((flags & MG_RUN_SKIP_SOURCE) && F_top) {
+        cy.push(N_max, const_cast<double *>(F_top));                  // the operators never write F
+    } else {
+        cy.push(N_max);                                               // :149
+        getSource(N_max, L, cy.top().F, min_x, min_y);                // :153 (outside the timer)
+    }
+    mgSync();
+
+    cudaStream_t stream = (cudaStream_t)mgStream();
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    const int launches0 = mgKernelLaunches();
+    const auto wall0 = std::chrono::steady_clock::now();
+    cudaEventRecord(ev0, stream);                                     // :156
+
+    NodeStream ns{tok, cur, pos, ladder, con_step, con_N, L};
+    int rc = interpret(cy, ns, 0);
     cudaEventRecord(ev1, stream);                                     // :429
     cy.harvest();
     const auto wall1 = std::chrono::steady_clock::now();
@@ -440,6 +487,40 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
 }
 
 }  // namespace
+
+// Runs, on ONE level owned by the caller (N, *U, *W, F: device grids), the node sub-stream that
+// starts at tok[*cur] and returns to that level (stops before the 1 node that would prolong above
+// it, before the code 2, or at the end).  Used by the slab driver for the levels agglomerated on
+// rank 0; execute == 0 parses only (ranks that hold no data) so that all ranks stay in step.
+// depth_offset = number of levels of the caller's stack above this one; *init_io = the level
+// stack's restart flag (linkedlist.h:41-44).
+extern "C" int mgRunSubcycle(const double *tok, int n_tok, int *cur, int *pos, const int *ladder, int n_ladder, int con_step,
+                             int con_N, double L, int N, double **U, double **W, double *F, int depth_offset, int *init_io,
+                             int flags, mgTraceRec *recs, int max_recs, int *n_recs_io, int execute)
+{
+    const std::vector<double> tokens(tok, tok + n_tok);
+    const std::vector<int> lad(ladder, ladder + n_ladder);
+    Cycle cy(flags | MG_RUN_FUSED | MG_RUN_QUIET, recs, max_recs);
+    cy.dry_ = !execute;
+    cy.depth_offset_ = (size_t)depth_offset;
+    cy.init_ = *init_io;
+    cy.n_recs_ = *n_recs_io;
+    Level l;
+    l.N = N;
+    l.borrowed = true;
+    if (execute) { l.U = *U; l.W = *W; l.F = F; }
+    cy.stack_.push_back(l);
+    NodeStream ns{tokens, (size_t)*cur, (size_t)*pos, lad, con_step, con_N, L};
+    const int rc = interpret(cy, ns, 1);
+    cy.harvest();
+    if (execute && !cy.stack_.empty()) { *U = cy.stack_[0].U; *W = cy.stack_[0].W; }
+    *cur = (int)ns.cur;
+    *pos = (int)ns.pos;
+    *init_io = cy.init_;
+    *n_recs_io = cy.n_recs_;
+    cy.stack_.clear();          // nothing here is owned by the Cycle
+    return rc;
+}
 
 extern "C" int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_top, mgTraceRec *recs,
                               int max_recs, mgCycleResult *res)
