@@ -314,7 +314,7 @@ WEAK_N = {1: 16384, 2: 23168, 4: 32768, 8: 46336}   # N^2 per GPU constant (1638
 def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, local, barrier, max_over_ranks, hbm_peak, peak_src):
     """Weak scaling of the row-slab driver: the grid grows with the GPU count so that every GPU keeps
     16384^2 fine points; one process per GPU, NCCL halo exchange, levels < 2048 rows on rank 0."""
-    threshold = 2048
+    threshold = int(os.environ.get("MG_DIST_THRESHOLD", "2048"))
     N = WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256) if args.nmax == 16384 else args.nmax
     n = N * N
     base_n = 16384 * 16384

@@ -183,6 +183,12 @@ int mgDistRunCycleFile(const char *path, int threshold, int flags, double *U_own
 int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, int *own_hi);
 int mgDistUploadSource(int N, int threshold, const double *F_slab_host);
 int mgDistDownloadSource(int N, double *F_slab_host);
+/* doSmoothing on row slabs, repeated (smoothing-only stress of BASELINE config 5): `reps` x `step`
+ * Jacobi sweeps from U = 0 on the analytic source, passes of <= 3 fused sweeps with one halo
+ * exchange each, error all-reduced per repetition.  N even, up to 65536.  Collective over the ranks
+ * of mgDistInit; on one GPU it works without it.  U_own_host (optional): the owned rows. */
+int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, double *error_out, double *U_own_host,
+                       int *own_lo, int *own_hi);
 /* The same slab algorithm with all `world` ranks emulated inside this process on the current GPU
  * (device-to-device copies instead of NCCL): lets the slab logic be verified on one GPU.
  * U_host (N_max^2) receives the assembled solution. */

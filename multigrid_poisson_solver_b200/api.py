@@ -73,6 +73,7 @@ ABI = {
     "mgDistUniqueId": (C.c_int, [_vp]),
     "mgDistInit": (C.c_int, [C.c_int, C.c_int, _vp]),
     "mgDistShutdown": (None, []),
+    "mgDistSmoothStress": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mgDistSourceSlab": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mgDistUploadSource": (C.c_int, [C.c_int, C.c_int, _vp]),
     "mgDistDownloadSource": (C.c_int, [C.c_int, _vp]),

@@ -901,6 +901,84 @@ int mgDistDownloadSource(int N, double *F_slab_host)
     return 0;
 }
 
+// doSmoothing on row slabs, repeated: `reps` times `step` Jacobi sweeps (passes of <= 3 fused sweeps,
+// one halo exchange per pass, error all-reduced once per repetition) on the analytic source grid,
+// starting from U = 0.  BASELINE config 5's smoothing-only stress; N up to 65536 (64-bit indexing).
+// Works without mgDistInit on one GPU.  U_own_host (optional) receives the rank's owned rows.
+int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, double *error_out, double *U_own_host, int *own_lo,
+                       int *own_hi)
+{
+    if (!ensure_ready()) return 10;
+    if (N % 2 || N < 64 || step < 1 || reps < 1) return 1;
+    EmuComm solo(1);
+    Comm &comm = g_nccl_comm ? static_cast<Comm &>(*g_nccl_comm) : static_cast<Comm &>(solo);
+    const int rank = g_nccl_comm ? g_nccl_comm->rank : 0;
+    Context &c = ctx();
+    const LevelGeom g = top_geometry(N, comm.world, 0);
+    if (comm.world > 1 && !g.dist) return 2;
+    const Slab sl = slab_of(g, rank);
+    const size_t bytes = (size_t)sl.rows * N * sizeof(double);
+    double *U = (double *)pool_alloc(bytes), *W = (double *)pool_alloc(bytes), *F = (double *)pool_alloc(bytes);
+    double *scal = (double *)pool_alloc(64 * sizeof(double));
+    if (!U || !W || !F || !scal) return 3;
+    launch_source(N, L, F, 0.0, 0.0, false, sl.row0, sl.rows);
+    check(cudaMemsetAsync(U, 0, bytes, c.stream), "memset");
+    check(cudaMemsetAsync(W, 0, bytes, c.stream), "memset");
+
+    auto exchange = [&](double *buf) {
+        if (!g.dist) return;
+        std::vector<Xfer> xs;
+        for (int k = 0; k + 1 < comm.world; ++k) {
+            if (k != rank && k + 1 != rank) continue;
+            const Slab a = slab_of(g, k), b = slab_of(g, k + 1);
+            const double *pa = k == rank ? buf : nullptr, *pb = k + 1 == rank ? buf : nullptr;
+            const int up_lo = std::max(a.own_hi - HALO, b.row0);
+            xs.push_back({k, k + 1, pa ? pa + (size_t)(up_lo - a.row0) * N : nullptr,
+                          pb ? const_cast<double *>(pb) + (size_t)(up_lo - b.row0) * N : nullptr, (size_t)(a.own_hi - up_lo) * N});
+            const int dn_hi = std::min(b.own_lo + HALO, a.row0 + a.rows);
+            xs.push_back({k + 1, k, pb ? pb + (size_t)(b.own_lo - b.row0) * N : nullptr,
+                          pa ? const_cast<double *>(pa) + (size_t)(b.own_lo - a.row0) * N : nullptr, (size_t)(dn_hi - b.own_lo) * N});
+        }
+        comm.transfer(xs);
+    };
+    const int n_pass = (step + 2) / 3;
+    auto one_rep = [&]() {
+        for (int k = 0; k < n_pass; ++k) {
+            const int S = step / n_pass + (k < step % n_pass ? 1 : 0);
+            exchange(U);
+            slab_pass(N, L, S, 0, U, F, W, sl, k + 1 == n_pass, scal, 0, nullptr, nullptr, 0, nullptr, nullptr);
+            std::swap(U, W);
+        }
+        if (comm.world > 1) comm.allreduce_sum({scal}, 1);
+    };
+    one_rep();                                   // warm-up (also NCCL connection set-up)
+    check(cudaMemsetAsync(U, 0, bytes, c.stream), "memset");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, c.stream);
+    for (int r = 0; r < reps; ++r) one_rep();
+    cudaEventRecord(e1, c.stream);
+    double s = 0.0;
+    check(cudaMemcpyAsync(&s, scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+    check(cudaStreamSynchronize(c.stream), "sync");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_rep) *ms_per_rep = ms / reps;
+    if (error_out) *error_out = (s + s) / (double)N / (double)N;
+    if (U_own_host) {
+        const size_t off = (size_t)(sl.own_lo - sl.row0) * N, cnt = (size_t)(sl.own_hi - sl.own_lo) * N;
+        check(cudaMemcpyAsync(U_own_host, U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
+        check(cudaStreamSynchronize(c.stream), "sync");
+    }
+    if (own_lo) *own_lo = sl.own_lo;
+    if (own_hi) *own_hi = sl.own_hi;
+    pool_free(U); pool_free(W); pool_free(F); pool_free(scal);
+    return c.err_code ? 10 : 0;
+}
+
 void mgDistShutdown(void)
 {
     if (g_nccl_comm) {

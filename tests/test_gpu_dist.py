@@ -75,3 +75,18 @@ def test_non_power_of_two_ladder(mg):
 
 def test_large_grid_slabs(mg):
     compare(mg, mg.cycles.v_cycle(4096, 8), 8, 1024)
+
+
+@pytest.mark.parametrize("N,step", [(256, 1), (512, 3), (1024, 7), (1000, 100)])
+def test_smoothing_stress_matches_do_smoothing(mg, N, step):
+    """mgDistSmoothStress on one GPU (one slab = the whole grid) == doSmoothing from U = 0."""
+    import ctypes as C
+    lib = mg.lib()
+    ms, err, lo, hi = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
+    U = np.empty(N * N)
+    rc = lib.mgDistSmoothStress(N, 1.0, step, 1, C.byref(ms), C.byref(err), U.ctypes.data, C.byref(lo), C.byref(hi))
+    assert rc == 0 and (lo.value, hi.value) == (0, N)
+    g = mg.GpuOps()
+    ref, eref = g.doSmoothing(N, 1.0, np.zeros(N * N), g.getSource(N), step)
+    assert np.array_equal(U, ref)
+    assert err.value == pytest.approx(eref, rel=1e-10)
