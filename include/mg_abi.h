@@ -139,6 +139,8 @@ typedef struct mgCycleResult {
 #define MG_RUN_QUIET 2          /* do not print the reference's stdout log */
 #define MG_RUN_SKIP_SOURCE 4    /* F of the top level is supplied by the caller (F_top, used in place, never written) */
 #define MG_RUN_NO_FINAL_ERROR 8 /* skip the analytic-error report after the node loop (mg_error = 0) */
+#define MG_RUN_DEFER_HARVEST 16 /* mgRunSubcycle only: do not synchronise at the end; the error scalars reach
+                                 * `recs` at the next mgSubcycleHarvest (or when the slot ring fills) */
 
 /* Runs a cycle file.  F_top (device, N_max^2) is used instead of getSource when
  * MG_RUN_SKIP_SOURCE is set.  U_top, if non-NULL (device, N_max^2), receives the
@@ -153,6 +155,8 @@ int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_t
 int mgRunSubcycle(const double *tok, int n_tok, int *cur, int *pos, const int *ladder, int n_ladder, int con_step,
                   int con_N, double L, int N, double **U, double **W, double *F, int depth_offset, int *init_io,
                   int flags, mgTraceRec *recs, int max_recs, int *n_recs_io, int execute);
+/* Synchronises and moves the scalars of sub-cycles run with MG_RUN_DEFER_HARVEST into their records. */
+void mgSubcycleHarvest(void);
 
 /* Same with HOST buffers: F_host (N_max^2, may be NULL -> getSource on device) is
  * copied to the device, the cycle runs, the solution is copied back into U_host. */

@@ -67,6 +67,7 @@ ABI = {
     "mgRunSubcycle": (C.c_int, [_dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                 C.c_double, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, C.c_int, C.POINTER(C.c_int), C.c_int,
                                 C.POINTER(TraceRec), C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "mgSubcycleHarvest": (None, []),
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),
     "mgDistPlan": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),

@@ -145,6 +145,9 @@ int mgInit(int device)
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
     bool ok = check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    ok = ok && check(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate (comm)");
     ok = ok && check(cudaMalloc(&c.counters, 64 * sizeof(unsigned int)), "cudaMalloc counters");
     ok = ok && check(cudaMemset(c.counters, 0, 64 * sizeof(unsigned int)), "cudaMemset counters");
     ok = ok && check(cudaMalloc(&c.gs_iters, 16 * sizeof(int)), "cudaMalloc gs_iters");
@@ -165,6 +168,7 @@ void mgShutdown(void)
     Context &c = ctx();
     if (!c.ready) return;
     cudaStreamSynchronize(c.stream);
+    cudaStreamSynchronize(c.comm_stream);
     for (auto &kv : c.free_lists)
         for (void *p : kv.second) cudaFree(p);
     for (auto &kv : c.live) cudaFree(kv.first);
@@ -179,6 +183,7 @@ void mgShutdown(void)
     cudaFree(c.scratch); cudaFree(c.partials); cudaFree(c.counters); cudaFree(c.gs_iters); cudaFree(c.dev_scalar);
     cudaFreeHost(c.slots_host);
     cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.comm_stream);
     c = Context();
 }
 

@@ -31,6 +31,7 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;   // highest priority; the slab driver issues all communication here
     bool ready = false;
 
     // error channel

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -55,23 +56,25 @@ public:
     int world = 1;
     std::vector<int> local;       // ranks living in this process
     bool is_local(int r) const { return std::find(local.begin(), local.end(), r) != local.end(); }
-    virtual void transfer(const std::vector<Xfer> &xs) = 0;
+    // both primitives are queued on `stream`; one communicator must only ever be driven from ONE
+    // stream at a time (NCCL operations of a communicator may not run concurrently)
+    virtual void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) = 0;
     // vals[i] = device pointer of local rank i; on return every one holds the sum over all ranks
-    virtual void allreduce_sum(const std::vector<double *> &vals, int n) = 0;
+    virtual void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) = 0;
 };
 
 class EmuComm : public Comm {
 public:
     explicit EmuComm(int g) { world = g; for (int r = 0; r < g; ++r) local.push_back(r); }
-    void transfer(const std::vector<Xfer> &xs) override
+    void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) override
     {
         for (const Xfer &x : xs)
-            if (x.count) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream), "emu transfer");
+            if (x.count) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, stream), "emu transfer");
     }
-    void allreduce_sum(const std::vector<double *> &vals, int n) override
+    void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) override
     {
         std::vector<double> acc((size_t)n, 0.0), tmp((size_t)n);
-        check(cudaStreamSynchronize(ctx().stream), "sync");
+        check(cudaStreamSynchronize(stream), "sync");
         for (double *v : vals) {   // rank order: the same association every run
             check(cudaMemcpy(tmp.data(), v, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost), "emu allreduce D2H");
             for (int i = 0; i < n; ++i) acc[i] += tmp[i];
@@ -118,23 +121,23 @@ public:
         fail(-32, std::string(what) + ": " + g_nccl.GetErrorString(r));
         return false;
     }
-    void transfer(const std::vector<Xfer> &xs) override
+    void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) override
     {
         ok(g_nccl.GroupStart(), "ncclGroupStart");
         for (const Xfer &x : xs) {
             if (!x.count) continue;
             if (x.src_rank == rank && x.dst_rank == rank) {
-                check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream), "self transfer");
+                check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, stream), "self transfer");
                 continue;
             }
-            if (x.src_rank == rank) ok(g_nccl.Send(x.src, x.count, ncclDouble, x.dst_rank, comm, ctx().stream), "ncclSend");
-            if (x.dst_rank == rank) ok(g_nccl.Recv(x.dst, x.count, ncclDouble, x.src_rank, comm, ctx().stream), "ncclRecv");
+            if (x.src_rank == rank) ok(g_nccl.Send(x.src, x.count, ncclDouble, x.dst_rank, comm, stream), "ncclSend");
+            if (x.dst_rank == rank) ok(g_nccl.Recv(x.dst, x.count, ncclDouble, x.src_rank, comm, stream), "ncclRecv");
         }
         ok(g_nccl.GroupEnd(), "ncclGroupEnd");
     }
-    void allreduce_sum(const std::vector<double *> &vals, int n) override
+    void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) override
     {
-        ok(g_nccl.AllReduce(vals[0], vals[0], (size_t)n, ncclDouble, ncclSum, comm, ctx().stream), "ncclAllReduce");
+        ok(g_nccl.AllReduce(vals[0], vals[0], (size_t)n, ncclDouble, ncclSum, comm, stream), "ncclAllReduce");
     }
 };
 std::unique_ptr<NcclComm> g_nccl_comm;
@@ -143,7 +146,7 @@ std::unique_ptr<NcclComm> g_nccl_comm;
 // fine row whose pair (f, f+1) produces coarse row c: the floor map of doRestriction
 // (MG_solver_CPU.cpp:661-662), with the two coarse boundary rows pinned to 0 and N-2 as in
 // mg_fused.cu.  Empty vector = the map is not injective / leaves the grid (pair not fusable).
-std::vector<int> fine_of_coarse_host(int N, int M)
+std::vector<int> fine_of_coarse_uncached(int N, int M)
 {
     std::vector<int> out;
     if (!(M >= 3 && M < N && N >= 4)) return out;
@@ -160,6 +163,15 @@ std::vector<int> fine_of_coarse_host(int N, int M)
     return out;
 }
 
+// every node of every cycle asks for the same few pairs: keep them (the map costs ~10 ns per coarse row)
+const std::vector<int> &fine_of_coarse_host(int N, int M)
+{
+    static std::map<std::pair<int, int>, std::vector<int>> cache;
+    auto it = cache.find({N, M});
+    if (it == cache.end()) it = cache.emplace(std::make_pair(N, M), fine_of_coarse_uncached(N, M)).first;
+    return it->second;
+}
+
 bool pair_fusable_host(int N, int M)
 {
     return N >= 4 && N % 2 == 0 && M >= 3 && (double)(N - 1) >= 1.2 * (double)(M - 1) && !fine_of_coarse_host(N, M).empty();
@@ -174,7 +186,7 @@ struct LevelGeom {
 // rank k owns the coarse rows whose lower fine row it owns
 std::vector<int> coarse_bounds(const LevelGeom &fine, int M, int world)
 {
-    const std::vector<int> foc = fine_of_coarse_host(fine.N, M);
+    const std::vector<int> &foc = fine_of_coarse_host(fine.N, M);
     std::vector<int> b((size_t)world + 1, M);
     int c = 0;
     for (int k = 0; k < world; ++k) {
@@ -235,7 +247,106 @@ struct RankState {
     double *scal = nullptr;   // device scalars: [0] error partial, [1] final abs-diff partial
 };
 
-struct Pending { int rec; int index; };
+// Halo rows of one array of a distributed level: rank k's last HALO owned rows go to rank k+1's
+// lower halo, rank k+1's first HALO owned rows to rank k's upper halo.  ptr(rank) = base of that
+// rank's local array (nullptr when the rank lives in another process).
+template <class Ptr>
+void halo_xfers(const LevelGeom &g, const Comm &comm, Ptr ptr, std::vector<Xfer> &xs)
+{
+    if (!g.dist) return;
+    const size_t N = g.N;
+    for (int k = 0; k + 1 < comm.world; ++k) {
+        if (!comm.is_local(k) && !comm.is_local(k + 1)) continue;
+        const Slab a = slab_of(g, k), b = slab_of(g, k + 1);
+        double *pa = ptr(k), *pb = ptr(k + 1);
+        const int up_lo = std::max(a.own_hi - HALO, b.row0);
+        xs.push_back({k, k + 1, pa ? pa + (size_t)(up_lo - a.row0) * N : nullptr, pb ? pb + (size_t)(up_lo - b.row0) * N : nullptr,
+                      (size_t)(a.own_hi - up_lo) * N});
+        const int dn_hi = std::min(b.own_lo + HALO, a.row0 + a.rows);
+        xs.push_back({k + 1, k, pb ? pb + (size_t)(b.own_lo - b.row0) * N : nullptr, pa ? pa + (size_t)(b.own_lo - a.row0) * N : nullptr,
+                      (size_t)(dn_hi - b.own_lo) * N});
+    }
+}
+
+// Stream protocol of the slab driver.  Kernels run on the compute stream `ms`; EVERY communication
+// primitive (halo exchange, gather/scatter, all-reduce, the scalar read-backs that follow an
+// all-reduce) is queued on the communication stream `cs`, so the communicator sees one ordered
+// stream.  A pass is launched in two parts: the edge row segments first -- they produce the rows
+// the neighbours' halos need -- then the interior; the halo exchange of the pass OUTPUT is queued
+// on cs behind the edge launch and runs while the interior launch computes.  The next pass waits
+// for that exchange (wait_halo) before it starts.  Because halos are refreshed when an array is
+// produced, no pass ever has to exchange before it reads.
+// Opt-in (MG_DIST_OVERLAP=1): measured on 2 x B200 it does not pay with NCCL transfers -- NCCL's
+// send/recv kernels need SMs, and the persistent interior launch holds every SM until it ends, so
+// the exchange starts late anyway.  By default both streams are the compute stream
+// and passes are launched whole, the exchange of the output right behind them.
+struct TwoStream {
+    cudaStream_t ms = nullptr, cs = nullptr, cs_hi = nullptr;   // cs: where communication goes right now (cs_hi or ms)
+    cudaEvent_t ev_join = nullptr, ev_edge = nullptr, ev_halo = nullptr;
+    bool overlap = true, halo_pending = false;
+    long long min_points = 0;   // slabs smaller than this run their communication in line on ms (MG_DIST_OVERLAP_MIN_POINTS)
+    TwoStream()
+    {
+        ms = ctx().stream;
+        cs_hi = ctx().comm_stream;
+        const char *e = getenv("MG_DIST_OVERLAP");
+        overlap = e && atoi(e) != 0;
+        if ((e = getenv("MG_DIST_OVERLAP_MIN_POINTS"))) min_points = atoll(e);
+        cs = overlap ? cs_hi : ms;
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_edge, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming);
+    }
+    ~TwoStream()
+    {
+        sync();
+        cudaEventDestroy(ev_join); cudaEventDestroy(ev_edge); cudaEventDestroy(ev_halo);
+    }
+    TwoStream(const TwoStream &) = delete;
+    TwoStream &operator=(const TwoStream &) = delete;
+    // communication queued after this sees everything the compute stream has been given so far
+    void to_comm()
+    {
+        if (cs == ms) return;
+        cudaEventRecord(ev_join, ms);
+        cudaStreamWaitEvent(cs, ev_join, 0);
+    }
+    // kernels queued after this see every communication queued so far
+    void to_compute()
+    {
+        halo_pending = false;
+        if (cs == ms) return;
+        cudaEventRecord(ev_join, cs);
+        cudaStreamWaitEvent(ms, ev_join, 0);
+    }
+    void halo_posted() { cudaEventRecord(ev_halo, cs); halo_pending = true; }
+    void wait_halo()
+    {
+        if (halo_pending && cs != ms) cudaStreamWaitEvent(ms, ev_halo, 0);
+        halo_pending = false;
+    }
+    void edge_done()   // the exchange queued next may start as soon as the edge launch has finished
+    {
+        if (cs == ms) return;
+        cudaEventRecord(ev_edge, ms);
+        cudaStreamWaitEvent(cs, ev_edge, 0);
+    }
+    void sync()
+    {
+        check(cudaStreamSynchronize(ms), "sync");
+        check(cudaStreamSynchronize(cs_hi), "sync (comm)");
+        halo_pending = false;
+    }
+    // choose where the communication of the next pass goes: overlapped on cs_hi, or in line on ms
+    // (small levels: the cross-stream hand-offs cost more than the exchange they would hide)
+    void select(bool overlapped)
+    {
+        cudaStream_t want = (overlap && overlapped) ? cs_hi : ms;
+        if (want == cs) return;
+        if (cs != ms) to_compute();   // leaving cs_hi: ms continues behind everything queued there
+        cs = want;                    // entering cs_hi: every primitive there starts with to_comm()/edge_done()
+    }
+};
 
 class DistCycle {
 public:
@@ -250,6 +361,7 @@ public:
     }
     ~DistCycle()
     {
+        ts.sync();                               // nothing queued may outlive the buffers
         while (!geom.empty()) pop();
         for (auto &st : ranks) pool_free(st.scal);
     }
@@ -259,6 +371,8 @@ public:
     std::vector<LevelGeom> geom;
     std::vector<RankState> ranks;
     int init_ = 1;
+    TwoStream ts;
+    int scal_used_ = 0;         // slots of the ranks' scal arrays holding error sums of this batch
 
     bool want_dist(int N) const { return comm.world > 1 && N >= threshold_; }
 
@@ -298,43 +412,72 @@ public:
         return induce_geometry(fine, M, comm.world, threshold_, coarse, why);
     }
 
-    // ---- halo exchange of one array of level `li` (which: 0 U, 1 F)
-    void exchange(int li, int which)
+    // ---- halo transfers of one array of level `li` (which: 0 U, 1 F, 2 W)
+    void add_halo(int li, int which, std::vector<Xfer> &xs)
     {
-        const LevelGeom &g = geom[li];
-        if (!g.dist) return;
-        std::vector<Xfer> xs;
-        auto ptr = [&](int rank) -> double * {
+        halo_xfers(geom[li], comm, [&](int rank) -> double * {
             for (auto &st : ranks)
-                if (st.rank == rank) return which == 0 ? st.lv[li].U : st.lv[li].F;
+                if (st.rank == rank) return which == 0 ? st.lv[li].U : which == 1 ? st.lv[li].F : st.lv[li].W;
             return nullptr;
-        };
-        const size_t N = g.N;
-        for (int k = 0; k + 1 < comm.world; ++k) {
-            if (!comm.is_local(k) && !comm.is_local(k + 1)) continue;
-            const Slab a = slab_of(g, k), b = slab_of(g, k + 1);
-            double *pa = ptr(k), *pb = ptr(k + 1);
-            // rank k's last HALO owned rows -> rank k+1's lower halo
-            const int up_lo = std::max(a.own_hi - HALO, b.row0);
-            xs.push_back({k, k + 1, pa ? pa + (size_t)(up_lo - a.row0) * N : nullptr, pb ? pb + (size_t)(up_lo - b.row0) * N : nullptr,
-                          (size_t)(a.own_hi - up_lo) * N});
-            // rank k+1's first HALO owned rows -> rank k's upper halo
-            const int dn_hi = std::min(b.own_lo + HALO, a.row0 + a.rows);
-            xs.push_back({k + 1, k, pb ? pb + (size_t)(b.own_lo - b.row0) * N : nullptr, pa ? pa + (size_t)(b.own_lo - a.row0) * N : nullptr,
-                          (size_t)(dn_hi - b.own_lo) * N});
-        }
-        comm.transfer(xs);
+        }, xs);
     }
 
-    void zero(double *p, const Slab &s, int N) { check(cudaMemsetAsync(p, 0, (size_t)s.rows * N * sizeof(double), ctx().stream), "memset"); }
+    void zero(double *p, const Slab &s, int N) { check(cudaMemsetAsync(p, 0, (size_t)s.rows * N * sizeof(double), ts.ms), "memset"); }
 
-    // sum the ranks' partials at scal[idx]; every local rank ends with the global sum
-    void allreduce(int idx)
+    // sum the ranks' partials at scal[idx .. idx+n); every local rank ends with the global sums (on ts.cs)
+    void allreduce(int idx, int n = 1)
     {
+        ts.to_comm();
         if (comm.world == 1) return;
         std::vector<double *> v;
         for (auto &st : ranks) v.push_back(st.scal + idx);
-        comm.allreduce_sum(v, 1);
+        comm.allreduce_sum(v, n, ts.cs);
+    }
+
+    // gather / scatter between rank 0 and the slabs: compute -> comm -> compute
+    void transfer_now(const std::vector<Xfer> &xs)
+    {
+        ts.to_comm();
+        comm.transfer(xs, ts.cs);
+        ts.to_compute();
+    }
+
+    // One fused pass over every local slab of distributed level `li`: S sweeps from U (in_mode 0),
+    // from zero (1) or from U + prolongation of the coarse slabs `uc` (2); optional red-parity error
+    // sum into scal[scal_idx]; optional restriction of the negated residual into `fc`.  The output
+    // (W, then swapped into U) and, with fc_halo, the coarse source get their halos refreshed by an
+    // exchange that overlaps the interior part of the pass.
+    void pass(int li, double L, int S, int in_mode, bool want_err, int scal_idx, int M, const std::vector<double *> &fc,
+              const std::vector<Slab> &fc_slab, bool fc_halo, int Nc, const std::vector<const double *> &uc,
+              const std::vector<Slab> &uc_slab)
+    {
+        const LevelGeom &g = geom[li];
+        const bool writes_U = !(S == 0 && in_mode == 0);
+        // the edge segments hold >= 24 fine rows per side: enough for 8 coarse halo rows up to ratio 2.5
+        ts.select((long long)g.N * (g.N / comm.world) >= ts.min_points);
+        const bool split = ts.cs != ts.ms && (!fc_halo || (double)(g.N - 1) <= 2.5 * (double)(M - 1));
+        auto launch = [&](int subset) {
+            for (size_t i = 0; i < ranks.size(); ++i) {
+                RankLevel &l = ranks[i].lv[li];
+                slab_pass(g.N, L, S, in_mode, l.U, l.F, writes_U ? l.W : nullptr, l.slab, want_err, ranks[i].scal + scal_idx, M,
+                          fc.empty() ? nullptr : fc[i], fc.empty() ? nullptr : &fc_slab[i], Nc, uc.empty() ? nullptr : uc[i],
+                          uc.empty() ? nullptr : &uc_slab[i], subset);
+            }
+        };
+        auto post_halo = [&]() {
+            std::vector<Xfer> xs;
+            if (writes_U) add_halo(li, 2, xs);
+            if (fc_halo) add_halo(li + 1, 1, xs);
+            if (xs.empty()) return;
+            ts.edge_done();
+            comm.transfer(xs, ts.cs);
+            ts.halo_posted();
+        };
+        ts.wait_halo();
+        if (split) { launch(1); post_halo(); launch(2); }
+        else       { launch(0); post_halo(); }
+        if (writes_U)
+            for (auto &st : ranks) std::swap(st.lv[li].U, st.lv[li].W);
     }
 };
 
@@ -403,34 +546,49 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     }
     check(cudaStreamSynchronize(c.stream), "sync");
 
-    // error scalars: device -> pinned ring, resolved after the final sync
-    std::vector<Pending> pending;
-    int n_recs = 0, slot = 0;
+    // Error sums of fixed-step nodes stay on the device as per-rank partials in consecutive scal slots;
+    // ONE all-reduce per batch (before an agglomerated sub-cycle, at the end, or when the slots run
+    // out) turns them into the trace records -- one collective instead of one per node.
+    int n_recs = 0;
     auto record = [&](int node, int N, int steps, double err) {
         const int r = n_recs++;
         if (recs && r < max_recs) { recs[r].node = node; recs[r].N = N; recs[r].steps = steps; recs[r].err = err; }
         return r;
     };
-    // Pending.rec >= 0: a raw red-parity sum (distributed node) or a GS iteration count;
-    // Pending.rec < 0 (-1-rec): an already normalised error from a single-GPU node on rank 0
+    constexpr int SCAL_BATCH = 48;
+    std::vector<std::pair<int, int>> deferred;     // (trace record, scal slot) holding a raw red-parity sum
     auto harvest = [&]() {
-        check(cudaStreamSynchronize(c.stream), "sync");
-        for (const Pending &p : pending) {
-            const double v = c.slots_host[p.index];
-            const int rec = p.rec < 0 ? -1 - p.rec : p.rec;
-            if (!recs || rec >= max_recs) continue;
-            if (recs[rec].node == 0) recs[rec].steps = (int)v;
-            else if (p.rec < 0) recs[rec].err = v;
-            else { const double N = recs[rec].N; recs[rec].err = (v + v) / N / N; }   // (sum1+sum2)/N/N, :621-622
+        if (cy.scal_used_ > 0) {
+            double sums[SCAL_BATCH];
+            cy.allreduce(0, cy.scal_used_);
+            check(cudaMemcpyAsync(sums, cy.ranks[0].scal, cy.scal_used_ * sizeof(double), cudaMemcpyDeviceToHost, cy.ts.cs), "D2H sums");
+            cy.ts.sync();
+            for (const auto &d : deferred) {
+                if (!recs || d.first >= max_recs) continue;
+                const double v = sums[d.second], N = recs[d.first].N;
+                recs[d.first].err = (v + v) / N / N;                      // (sum1+sum2)/N/N, :621-622
+            }
+            deferred.clear();
+            cy.scal_used_ = 0;
         }
-        pending.clear();
-        slot = 0;
+        cy.ts.sync();
+        mgSubcycleHarvest();                     // scalars of the agglomerated sub-cycles (rank 0)
     };
-    auto defer_scalar = [&](int rec, const double *dev_value) {   // async copy of a device scalar into the pinned ring
-        if (slot >= MG_SCALAR_SLOTS - 8) harvest();
-        check(cudaMemcpyAsync(c.slots_host + slot, dev_value, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H scalar");
-        pending.push_back({rec, slot++});
+    auto next_scal = [&]() {
+        if (cy.scal_used_ == SCAL_BATCH) harvest();
+        return cy.scal_used_++;
     };
+    // all-reduce scal[idx] and wait for the value on the host (trigger loops)
+    auto reduced_now = [&](int idx) {
+        cy.allreduce(idx);
+        double s = 0.0;
+        check(cudaMemcpyAsync(&s, cy.ranks[0].scal + idx, sizeof(double), cudaMemcpyDeviceToHost, cy.ts.cs), "D2H");
+        check(cudaStreamSynchronize(cy.ts.cs), "sync");
+        return s;
+    };
+    const std::vector<double *> no_fc;
+    const std::vector<const double *> no_uc;
+    const std::vector<Slab> no_slab;
 
     // one node's smoothing on a distributed level: `step` sweeps (or the trigger loop), optional
     // restriction into the next level; returns sweeps done and records the error
@@ -441,6 +599,19 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     const auto wall0 = std::chrono::steady_clock::now();
     cudaEventRecord(ev0, c.stream);
 
+    // MG_DIST_TRACE=1: per-node time line (device time on the compute stream, host enqueue time)
+    struct Mark { const char *what; int N; cudaEvent_t ev; std::chrono::steady_clock::time_point host; };
+    std::vector<Mark> marks;
+    const bool tracing = getenv("MG_DIST_TRACE") && atoi(getenv("MG_DIST_TRACE")) != 0;
+    auto mark = [&](const char *what, int N) {
+        if (!tracing) return;
+        Mark m{what, N, nullptr, std::chrono::steady_clock::now()};
+        cudaEventCreate(&m.ev);
+        cudaEventRecord(m.ev, c.stream);
+        marks.push_back(m);
+    };
+    mark("start", N_max);
+
     int rc = 0, node = 0;
     std::string why;
     while (have(1)) {
@@ -448,7 +619,6 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
         // alone is run by the single-GPU interpreter (fused nodes + coarse tail kernel) on rank 0;
         // the other ranks parse the same nodes without executing them.
         if (!cy.geom.back().dist && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
-            harvest();                                   // the sub-interpreter uses the scalar-slot ring too
             const int li = (int)cy.geom.size() - 1;
             int icur = (int)cur, ipos = (int)pos, n_rec_io = n_recs, init_io = cy.init_;
             int sub_rc = 0;
@@ -456,13 +626,14 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
                 RankLevel &l = st.lv[li];
                 int c2 = (int)cur, p2 = (int)pos, r2 = n_recs, i2 = cy.init_;
                 sub_rc = mgRunSubcycle(tok.data(), (int)tok.size(), &c2, &p2, ladder.data(), (int)ladder.size(), con_step, con_N, L,
-                                       cy.geom[li].N, &l.U, &l.W, l.F, li, &i2, flags,
+                                       cy.geom[li].N, &l.U, &l.W, l.F, li, &i2, flags | MG_RUN_DEFER_HARVEST,
                                        (st.rank == 0 || !comm.is_local(0)) ? recs : nullptr, max_recs, &r2, st.rank == 0 ? 1 : 0);
                 icur = c2; ipos = p2; n_rec_io = r2; init_io = i2;
                 if (sub_rc) break;
             }
             if (sub_rc) { rc = sub_rc; break; }
             cur = (size_t)icur; pos = (size_t)ipos; n_recs = n_rec_io; cy.init_ = init_io;
+            mark("sub-cycle", cy.geom[li].N);
             continue;
         }
         node = next_int();
@@ -474,6 +645,7 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             if (con_N == 0) { if (!have(1)) { rc = 3; break; } next_N = next_int(); }
             else { if (pos + 1 >= ladder.size()) { rc = 4; break; } next_N = ladder[++pos]; }
             if (step == 0) continue;
+            // (agglomerated levels never get here: the sub-cycle interpreter above took the node)
             const int li = (int)cy.geom.size() - 1;
             const LevelGeom fine = cy.geom[li];
             const bool zero_init = !cy.restart_top();
@@ -481,114 +653,49 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             if (!cy.induce(fine, next_N, coarse, why)) { fail(-40, why); rc = 20; break; }
             cy.push(coarse);
 
-            if (!fine.dist) {   // agglomerated: the single-GPU fused node on rank 0
-                for (auto &st : cy.ranks) {
-                    if (st.rank != 0) continue;
-                    RankLevel &l = st.lv[li], &nl = st.lv[li + 1];
-                    int done = step;
-                    if (step > 0) {
-                        double *r = down_leg(fine.N, L, l.U, l.W, l.F, step, zero_init, next_N, nl.F, nullptr);
-                        if (r != l.U) std::swap(l.U, l.W);
-                        // down_leg leaves (S+S)/N/N in dev_scalar; undo to the raw convention: store e*N*N/2
-                        const int rr = record(-1, fine.N, step, 0.0);
-                        if (slot >= MG_SCALAR_SLOTS - 8) harvest();
-                        check(cudaMemcpyAsync(c.slots_host + slot, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-                        pending.push_back({-1 - rr, slot++});
-                    } else {    // trigger loop
-                        if (zero_init) cy.zero(l.U, l.slab, fine.N);
-                        double slope = TRIGGER + 1.0, prev = 0.0, err = 0.0;
-                        done = 0;
-                        while (slope > TRIGGER) {
-                            double *r = smooth_out_of_place(fine.N, L, l.U, l.W, l.U, l.F, 1, false, c.dev_scalar, nullptr);
-                            if (r != l.U) std::swap(l.U, l.W);
-                            check(cudaMemcpyAsync(&err, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-                            check(cudaStreamSynchronize(c.stream), "sync");
-                            ++done;
-                            if (done > 1) slope = std::fabs(err - prev);
-                            prev = err;
-                            if (c.err_code) break;
-                        }
-                        down_leg(fine.N, L, l.U, l.W, l.F, 0, false, next_N, nl.F, nullptr);
-                        record(-1, fine.N, done, err);
-                    }
-                }
-                if (!comm.is_local(0) && step > 0) record(-1, fine.N, step, 0.0);
-                if (!comm.is_local(0) && step < 0) record(-1, fine.N, 0, 0.0);
-                if (!quiet) fputs(kRestrictArt, stdout);
-                continue;
-            }
-
-            // ---- distributed fine level
             // F_c target per rank: the coarse slab's F if the coarse level is distributed, else a
             // temporary holding exactly the rank's coarse rows (rank 0 writes into the full array)
             const std::vector<int> cb = coarse_bounds(fine, next_N, comm.world);
-            std::vector<double *> fc_tmp(cy.ranks.size(), nullptr);
+            std::vector<double *> fc_tmp(cy.ranks.size(), nullptr), fc(cy.ranks.size(), nullptr);
             std::vector<Slab> fc_slab(cy.ranks.size());
             for (size_t i = 0; i < cy.ranks.size(); ++i) {
                 RankState &st = cy.ranks[i];
-                if (coarse.dist) { fc_slab[i] = st.lv[li + 1].slab; continue; }
-                if (st.rank == 0) { fc_slab[i] = st.lv[li + 1].slab; continue; }
+                fc[i] = st.lv[li + 1].F;
+                fc_slab[i] = st.lv[li + 1].slab;
+                if (coarse.dist || st.rank == 0) continue;
                 fc_slab[i].row0 = fc_slab[i].own_lo = cb[st.rank];
                 fc_slab[i].own_hi = cb[st.rank + 1];
                 fc_slab[i].rows = cb[st.rank + 1] - cb[st.rank];
-                fc_tmp[i] = (double *)pool_alloc((size_t)std::max(1, fc_slab[i].rows) * next_N * sizeof(double));
+                fc[i] = fc_tmp[i] = (double *)pool_alloc((size_t)std::max(1, fc_slab[i].rows) * next_N * sizeof(double));
             }
-            auto fc_ptr = [&](size_t i) { return fc_tmp[i] ? fc_tmp[i] : cy.ranks[i].lv[li + 1].F; };
 
-            int done = 0;
-            double err_host = 0.0;
             if (step > 0) {
-                // passes of at most 3 sweeps; halos of the pass input must be current
-                const int n_pass = (step + 2) / 3;
+                // passes of at most 3 sweeps; the last one also restricts
+                const int n_pass = (step + 2) / 3, idx = next_scal();
                 for (int k = 0; k < n_pass; ++k) {
                     const int S = step / n_pass + (k < step % n_pass ? 1 : 0);
                     const bool first = k == 0, last = k + 1 == n_pass;
-                    const int in_mode = (first && zero_init) ? 1 : 0;
-                    if (in_mode == 0) cy.exchange(li, 0);
-                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                        RankLevel &l = cy.ranks[i].lv[li];
-                        slab_pass(fine.N, L, S, in_mode, l.U, l.F, l.W, l.slab, last, cy.ranks[i].scal, next_N,
-                                  last ? fc_ptr(i) : nullptr, last ? &fc_slab[i] : nullptr, 0, nullptr, nullptr);
-                        std::swap(l.U, l.W);
-                    }
+                    if (last) cy.pass(li, L, S, (first && zero_init) ? 1 : 0, true, idx, next_N, fc, fc_slab, coarse.dist, 0, no_uc, no_slab);
+                    else      cy.pass(li, L, S, (first && zero_init) ? 1 : 0, false, idx, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
                 }
-                done = step;
-                cy.allreduce(0);
-                const int rr = record(-1, fine.N, step, 0.0);
-                defer_scalar(rr, cy.ranks[0].scal);
+                deferred.push_back({record(-1, fine.N, step, 0.0), idx});
             } else {   // trigger loop: the scalar is needed after every sweep
-                double slope = TRIGGER + 1.0, prev = 0.0;
-                bool first = true;
+                double slope = TRIGGER + 1.0, prev = 0.0, err_host = 0.0;
+                int done = 0;
                 while (slope > TRIGGER) {
-                    const int in_mode = (first && zero_init) ? 1 : 0;
-                    if (in_mode == 0) cy.exchange(li, 0);
-                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                        RankLevel &l = cy.ranks[i].lv[li];
-                        slab_pass(fine.N, L, 1, in_mode, l.U, l.F, l.W, l.slab, true, cy.ranks[i].scal, 0, nullptr, nullptr, 0, nullptr, nullptr);
-                        std::swap(l.U, l.W);
-                    }
-                    cy.allreduce(0);
-                    double s = 0.0;
-                    check(cudaMemcpyAsync(&s, cy.ranks[0].scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-                    check(cudaStreamSynchronize(c.stream), "sync");
+                    const int idx = next_scal();
+                    cy.pass(li, L, 1, (done == 0 && zero_init) ? 1 : 0, true, idx, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
+                    const double s = reduced_now(idx);
                     err_host = (s + s) / fine.N / fine.N;
                     ++done;
                     if (done > 1) slope = std::fabs(err_host - prev);
                     prev = err_host;
-                    first = false;
                     if (c.err_code) break;
                 }
-                cy.exchange(li, 0);
-                for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                    RankLevel &l = cy.ranks[i].lv[li];
-                    slab_pass(fine.N, L, 0, 0, l.U, l.F, nullptr, l.slab, false, nullptr, next_N, fc_ptr(i), &fc_slab[i], 0, nullptr, nullptr);
-                }
+                cy.pass(li, L, 0, 0, false, 0, next_N, fc, fc_slab, coarse.dist, 0, no_uc, no_slab);   // residual + restriction only
                 record(-1, fine.N, done, err_host);
             }
-            // ---- make the coarse source complete
-            if (coarse.dist) {
-                cy.exchange(li + 1, 1);
-            } else {           // gather the slabs' coarse rows into rank 0's full grid
+            if (!coarse.dist) {           // gather the slabs' coarse rows into rank 0's full grid
                 std::vector<Xfer> xs;
                 for (int k = 1; k < comm.world; ++k) {
                     const double *src = nullptr;
@@ -600,34 +707,17 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
                     if (!comm.is_local(k) && !comm.is_local(0)) continue;
                     xs.push_back({k, 0, src, dst, (size_t)(cb[k + 1] - cb[k]) * next_N});
                 }
-                comm.transfer(xs);
+                cy.transfer_now(xs);
             }
             for (double *p : fc_tmp) pool_free(p);
             if (!quiet) fputs(kRestrictArt, stdout);
+            mark(coarse.dist ? "down" : "down+gather", fine.N);
         } else if (node == 0) {
-            double target; int option;
             if (!have(2)) { rc = 3; break; }
-            target = tok[cur++];
-            option = next_int();
-            const int li = (int)cy.geom.size() - 1;
-            if (cy.geom[li].dist) { fail(-41, "the exact solver runs on an agglomerated level: lower the coarsest size or raise the threshold"); rc = 21; break; }
-            const int rr = record(0, cy.geom[li].N, -1, 0.0);
-            for (auto &st : cy.ranks) {
-                if (st.rank != 0) continue;
-                RankLevel &l = st.lv[li];
-                if (slot >= MG_SCALAR_SLOTS - 8) harvest();
-                if (option == 0) launch_inverse_matrix(cy.geom[li].N, L, l.U, l.F);
-                else if (option == 1) {
-                    launch_gauss_seidel(cy.geom[li].N, L, l.U, l.F, target, c.slots_dev + slot);
-                    pending.push_back({rr, slot++});
-                }
-            }
-            if (!quiet) {
-                printf("          ~Exact Solver~\nCurrent Grid Size N = %d\n", cy.geom[li].N);
-                if (option == 0) printf("   Use Exact Solver = Inverse Matrix\n");
-                if (option == 1) printf("   Use Exact Solver = GaussSeidel Even / Odd\n");
-                printf("       Target Error = %.3e\n", target);
-            }
+            // an exact solve on an agglomerated level is part of the sub-cycle taken above
+            fail(-41, "the exact solver runs on an agglomerated level: lower the coarsest size or raise the threshold");
+            rc = 21;
+            break;
         } else if (node == 1) {
             int step;
             if (con_step == 0) { if (!have(1)) { rc = 3; break; } step = next_int(); } else step = con_step;
@@ -635,105 +725,52 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             if (cy.geom.size() < 2) { rc = 5; break; }
             const int lc = (int)cy.geom.size() - 1, lf = lc - 1;
             const LevelGeom coarse = cy.geom[lc], fine = cy.geom[lf];
+            if (!fine.dist) { rc = 7; break; }   // cannot happen: levels below an agglomerated one belong to the sub-cycle
 
-            if (!fine.dist) {
-                for (auto &st : cy.ranks) {
-                    if (st.rank != 0) continue;
-                    RankLevel &l = st.lv[lf], &cl = st.lv[lc];
-                    double *r = up_leg(coarse.N, cl.U, fine.N, L, l.U, l.W, l.F, step > 0 ? step : 0, nullptr);
-                    if (r != l.U) std::swap(l.U, l.W);
-                    if (step > 0) {
-                        const int rr = record(1, fine.N, step, 0.0);
-                        if (slot >= MG_SCALAR_SLOTS - 8) harvest();
-                        check(cudaMemcpyAsync(c.slots_host + slot, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-                        pending.push_back({-1 - rr, slot++});
-                    } else if (step < 0) {
-                        double slope = TRIGGER + 1.0, prev = 0.0, err = 0.0;
-                        int done = 0;
-                        while (slope > TRIGGER) {
-                            double *q = smooth_out_of_place(fine.N, L, l.U, l.W, l.U, l.F, 1, false, c.dev_scalar, nullptr);
-                            if (q != l.U) std::swap(l.U, l.W);
-                            check(cudaMemcpyAsync(&err, c.dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-                            check(cudaStreamSynchronize(c.stream), "sync");
-                            ++done;
-                            if (done > 1) slope = std::fabs(err - prev);
-                            prev = err;
-                            if (c.err_code) break;
-                        }
-                        record(1, fine.N, done, err);
-                    } else record(1, fine.N, 0, 0.0);
-                }
-                if (!comm.is_local(0)) record(1, fine.N, step > 0 ? step : 0, 0.0);
-                if (!quiet) fputs(kProlongArt, stdout);
-                cy.pop();
-                continue;
-            }
-
-            // ---- distributed fine level: U_c rows with halo on every rank, current U_f halos
+            // ---- U_c rows with halo on every rank (halos of distributed arrays are current by construction)
             std::vector<double *> uc_tmp(cy.ranks.size(), nullptr);
+            std::vector<const double *> uc(cy.ranks.size(), nullptr);
             std::vector<Slab> uc_slab(cy.ranks.size());
-            if (coarse.dist) {
-                cy.exchange(lc, 0);
-                for (size_t i = 0; i < cy.ranks.size(); ++i) uc_slab[i] = cy.ranks[i].lv[lc].slab;
-            } else {
+            for (size_t i = 0; i < cy.ranks.size(); ++i) { uc[i] = cy.ranks[i].lv[lc].U; uc_slab[i] = cy.ranks[i].lv[lc].slab; }
+            if (!coarse.dist) {          // scatter rank 0's full coarse grid: each rank gets its rows plus halo
                 const std::vector<int> cb = coarse_bounds(fine, coarse.N, comm.world);
                 std::vector<Xfer> xs;
                 const double *full = nullptr;
                 for (auto &st : cy.ranks) if (st.rank == 0) full = st.lv[lc].U;
-                for (int k = 0; k < comm.world; ++k) {
+                for (int k = 1; k < comm.world; ++k) {
                     Slab s;
                     s.own_lo = cb[k]; s.own_hi = cb[k + 1];
                     s.row0 = std::max(0, cb[k] - HALO);
                     s.rows = std::min(coarse.N, cb[k + 1] + HALO) - s.row0;
+                    double *dst = nullptr;
                     for (size_t i = 0; i < cy.ranks.size(); ++i) {
                         if (cy.ranks[i].rank != k) continue;
-                        if (k == 0) { uc_slab[i] = cy.ranks[i].lv[lc].slab; continue; }
                         uc_slab[i] = s;
-                        uc_tmp[i] = (double *)pool_alloc((size_t)s.rows * coarse.N * sizeof(double));
+                        uc[i] = dst = uc_tmp[i] = (double *)pool_alloc((size_t)s.rows * coarse.N * sizeof(double));
                     }
-                    if (k == 0 || (!comm.is_local(k) && !comm.is_local(0))) continue;
-                    double *dst = nullptr;
-                    for (size_t i = 0; i < cy.ranks.size(); ++i) if (cy.ranks[i].rank == k) dst = uc_tmp[i];
+                    if (!comm.is_local(k) && !comm.is_local(0)) continue;
                     xs.push_back({0, k, full ? full + (size_t)s.row0 * coarse.N : nullptr, dst, (size_t)s.rows * coarse.N});
                 }
-                comm.transfer(xs);
+                cy.transfer_now(xs);
             }
-            auto uc_ptr = [&](size_t i) -> const double * { return uc_tmp[i] ? uc_tmp[i] : cy.ranks[i].lv[lc].U; };
-            cy.exchange(lf, 0);
 
-            int done = 0;
-            double err_host = 0.0;
             const int fixed = step > 0 ? step : 0;
-            const int n_pass = std::max(1, (fixed + 2) / 3);
+            const int n_pass = std::max(1, (fixed + 2) / 3), idx = next_scal();
             for (int k = 0; k < n_pass; ++k) {
                 const int S = fixed / n_pass + (k < fixed % n_pass ? 1 : 0);
                 const bool first = k == 0, last = k + 1 == n_pass;
-                if (!first) cy.exchange(lf, 0);
-                for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                    RankLevel &l = cy.ranks[i].lv[lf];
-                    slab_pass(fine.N, L, S, first ? 2 : 0, l.U, l.F, l.W, l.slab, last && step > 0, cy.ranks[i].scal, 0, nullptr, nullptr,
-                              coarse.N, first ? uc_ptr(i) : nullptr, first ? &uc_slab[i] : nullptr);
-                    std::swap(l.U, l.W);
-                }
+                if (first) cy.pass(lf, L, S, 2, last && step > 0, idx, 0, no_fc, no_slab, false, coarse.N, uc, uc_slab);
+                else       cy.pass(lf, L, S, 0, last && step > 0, idx, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
             }
             if (step > 0) {
-                done = step;
-                cy.allreduce(0);
-                const int rr = record(1, fine.N, step, 0.0);
-                defer_scalar(rr, cy.ranks[0].scal);
+                deferred.push_back({record(1, fine.N, step, 0.0), idx});
             } else if (step < 0) {
-                double slope = TRIGGER + 1.0, prev = 0.0;
+                double slope = TRIGGER + 1.0, prev = 0.0, err_host = 0.0;
+                int done = 0;
                 while (slope > TRIGGER) {
-                    cy.exchange(lf, 0);
-                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                        RankLevel &l = cy.ranks[i].lv[lf];
-                        slab_pass(fine.N, L, 1, 0, l.U, l.F, l.W, l.slab, true, cy.ranks[i].scal, 0, nullptr, nullptr, 0, nullptr, nullptr);
-                        std::swap(l.U, l.W);
-                    }
-                    cy.allreduce(0);
-                    double s = 0.0;
-                    check(cudaMemcpyAsync(&s, cy.ranks[0].scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-                    check(cudaStreamSynchronize(c.stream), "sync");
+                    const int j = next_scal();
+                    cy.pass(lf, L, 1, 0, true, j, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
+                    const double s = reduced_now(j);
                     err_host = (s + s) / fine.N / fine.N;
                     ++done;
                     if (done > 1) slope = std::fabs(err_host - prev);
@@ -745,11 +782,21 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             for (double *p : uc_tmp) pool_free(p);
             if (!quiet) fputs(kProlongArt, stdout);
             cy.pop();
+            mark(coarse.dist ? "up" : "scatter+up", fine.N);
         } else { rc = 6; break; }
     }
+    cy.ts.to_compute();                          // the timed span ends when both streams have drained
     cudaEventRecord(ev1, c.stream);
     harvest();
     const auto wall1 = std::chrono::steady_clock::now();
+    for (size_t i = 1; i < marks.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, marks[i - 1].ev, marks[i].ev);
+        if (comm.is_local(0))
+            fprintf(stderr, "[mg trace] %-12s N=%-6d device %8.3f ms   host enqueue %8.3f ms\n", marks[i].what, marks[i].N, ms,
+                    std::chrono::duration<double, std::milli>(marks[i].host - marks[i - 1].host).count());
+    }
+    for (Mark &m : marks) cudaEventDestroy(m.ev);
     if (c.err_code && rc == 0) rc = 10;
 
     if (res) {
@@ -771,16 +818,13 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
         if (res && !(flags & MG_RUN_NO_FINAL_ERROR)) {
             for (auto &st : cy.ranks) {
                 RankLevel &l = st.lv[0];
-                check(cudaMemsetAsync(st.scal + 1, 0, sizeof(double), c.stream), "memset");
+                check(cudaMemsetAsync(st.scal + 60, 0, sizeof(double), c.stream), "memset");
                 if (!l.present) continue;
                 launch_source(g.N, L, l.W, min_x, min_y, true, l.slab.row0, l.slab.rows);
                 const size_t off = (size_t)(l.slab.own_lo - l.slab.row0) * g.N, cnt = (size_t)(l.slab.own_hi - l.slab.own_lo) * g.N;
-                launch_mean_abs_diff(cnt, l.W + off, l.U + off, 1.0, st.scal + 1);
+                launch_mean_abs_diff(cnt, l.W + off, l.U + off, 1.0, st.scal + 60);
             }
-            if (g.dist) cy.allreduce(1);
-            double s = 0.0;
-            check(cudaMemcpyAsync(&s, cy.ranks[0].scal + 1, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
-            check(cudaStreamSynchronize(c.stream), "sync");
+            const double s = reduced_now(60);   // ranks without a share contribute 0
             res->mg_error = s / ((double)g.N * (double)g.N);
         }
         // ---- solution out
@@ -925,42 +969,43 @@ int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, 
     check(cudaMemsetAsync(U, 0, bytes, c.stream), "memset");
     check(cudaMemsetAsync(W, 0, bytes, c.stream), "memset");
 
-    auto exchange = [&](double *buf) {
-        if (!g.dist) return;
-        std::vector<Xfer> xs;
-        for (int k = 0; k + 1 < comm.world; ++k) {
-            if (k != rank && k + 1 != rank) continue;
-            const Slab a = slab_of(g, k), b = slab_of(g, k + 1);
-            const double *pa = k == rank ? buf : nullptr, *pb = k + 1 == rank ? buf : nullptr;
-            const int up_lo = std::max(a.own_hi - HALO, b.row0);
-            xs.push_back({k, k + 1, pa ? pa + (size_t)(up_lo - a.row0) * N : nullptr,
-                          pb ? const_cast<double *>(pb) + (size_t)(up_lo - b.row0) * N : nullptr, (size_t)(a.own_hi - up_lo) * N});
-            const int dn_hi = std::min(b.own_lo + HALO, a.row0 + a.rows);
-            xs.push_back({k + 1, k, pb ? pb + (size_t)(b.own_lo - b.row0) * N : nullptr,
-                          pa ? const_cast<double *>(pa) + (size_t)(b.own_lo - a.row0) * N : nullptr, (size_t)(dn_hi - b.own_lo) * N});
-        }
-        comm.transfer(xs);
-    };
+    TwoStream ts;
     const int n_pass = (step + 2) / 3;
+    int rot = 0;
     auto one_rep = [&]() {
+        if (++rot == 48) { ts.sync(); rot = 1; }          // scal slots still queued for an all-reduce
         for (int k = 0; k < n_pass; ++k) {
             const int S = step / n_pass + (k < step % n_pass ? 1 : 0);
-            exchange(U);
-            slab_pass(N, L, S, 0, U, F, W, sl, k + 1 == n_pass, scal, 0, nullptr, nullptr, 0, nullptr, nullptr);
+            const bool last = k + 1 == n_pass;
+            std::vector<Xfer> xs;
+            halo_xfers(g, comm, [&](int r) -> double * { return r == rank ? W : nullptr; }, xs);
+            ts.wait_halo();
+            if (ts.cs != ts.ms && !xs.empty()) {
+                slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, 1);
+                ts.edge_done();
+                comm.transfer(xs, ts.cs);
+                ts.halo_posted();
+                slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, 2);
+            } else {
+                slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, 0);
+                if (!xs.empty()) { comm.transfer(xs, ts.cs); ts.halo_posted(); }
+            }
             std::swap(U, W);
         }
-        if (comm.world > 1) comm.allreduce_sum({scal}, 1);
+        if (comm.world > 1) { ts.to_comm(); comm.allreduce_sum({scal + rot}, 1, ts.cs); }
     };
     one_rep();                                   // warm-up (also NCCL connection set-up)
+    ts.to_compute();                             // the warm-up's last halo exchange lands before the reset
     check(cudaMemsetAsync(U, 0, bytes, c.stream), "memset");
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, c.stream);
     for (int r = 0; r < reps; ++r) one_rep();
+    ts.to_compute();
     cudaEventRecord(e1, c.stream);
     double s = 0.0;
-    check(cudaMemcpyAsync(&s, scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+    check(cudaMemcpyAsync(&s, scal + rot, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
     check(cudaStreamSynchronize(c.stream), "sync");
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);

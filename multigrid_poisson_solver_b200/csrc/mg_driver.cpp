@@ -494,17 +494,39 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
 // rank 0; execute == 0 parses only (ranks that hold no data) so that all ranks stay in step.
 // depth_offset = number of levels of the caller's stack above this one; *init_io = the level
 // stack's restart flag (linkedlist.h:41-44).
+// Scalars of sub-cycles run with MG_RUN_DEFER_HARVEST: still in the pinned slot ring, owed to g_carry_recs.
+namespace {
+std::vector<Pending> g_carry;
+int g_carry_slot = 0, g_carry_max = 0;
+mgTraceRec *g_carry_recs = nullptr;
+}  // namespace
+
+extern "C" void mgSubcycleHarvest(void)
+{
+    if (g_carry.empty()) { g_carry_slot = 0; return; }
+    Cycle cy(MG_RUN_FUSED | MG_RUN_QUIET, g_carry_recs, g_carry_max);
+    cy.pending_.swap(g_carry);
+    cy.harvest();
+    g_carry_slot = 0;
+}
+
 extern "C" int mgRunSubcycle(const double *tok, int n_tok, int *cur, int *pos, const int *ladder, int n_ladder, int con_step,
                              int con_N, double L, int N, double **U, double **W, double *F, int depth_offset, int *init_io,
                              int flags, mgTraceRec *recs, int max_recs, int *n_recs_io, int execute)
 {
+    const bool defer = (flags & MG_RUN_DEFER_HARVEST) && execute;
+    if (execute && !g_carry.empty() && (!defer || recs != g_carry_recs)) mgSubcycleHarvest();   // another caller's leftovers
     const std::vector<double> tokens(tok, tok + n_tok);
     const std::vector<int> lad(ladder, ladder + n_ladder);
-    Cycle cy(flags | MG_RUN_FUSED | MG_RUN_QUIET, recs, max_recs);
+    Cycle cy((flags & ~MG_RUN_DEFER_HARVEST) | MG_RUN_FUSED | MG_RUN_QUIET, recs, max_recs);
     cy.dry_ = !execute;
     cy.depth_offset_ = (size_t)depth_offset;
     cy.init_ = *init_io;
     cy.n_recs_ = *n_recs_io;
+    if (defer) {                // continue the slot ring where the previous deferred sub-cycle stopped
+        cy.pending_.swap(g_carry);
+        cy.slot_ = g_carry_slot;
+    }
     Level l;
     l.N = N;
     l.borrowed = true;
@@ -512,7 +534,12 @@ extern "C" int mgRunSubcycle(const double *tok, int n_tok, int *cur, int *pos, c
     cy.stack_.push_back(l);
     NodeStream ns{tokens, (size_t)*cur, (size_t)*pos, lad, con_step, con_N, L};
     const int rc = interpret(cy, ns, 1);
-    cy.harvest();
+    if (defer) {
+        g_carry.swap(cy.pending_);
+        g_carry_slot = cy.slot_;
+        g_carry_recs = recs;
+        g_carry_max = max_recs;
+    } else cy.harvest();
     if (execute && !cy.stack_.empty()) { *U = cy.stack_[0].U; *W = cy.stack_[0].W; }
     *cur = (int)ns.cur;
     *pos = (int)ns.pos;

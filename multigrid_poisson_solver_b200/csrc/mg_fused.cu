@@ -72,7 +72,8 @@ int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that ha
 
 // Task geometry, persistent grid and launch shared by the two streaming kernels.
 template <typename Kernel>
-void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int min_ctas, int smem_bytes, bool err, bool &opted_in)
+void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int min_ctas, int smem_bytes, bool err, int lead_rows,
+                          bool &opted_in)
 {
     Context &c = ctx();
     const int N = p.N;
@@ -81,18 +82,48 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
     // cost (2S+3)/H of extra work, so at least 32 rows), otherwise as many tasks as 16-row
     // segments allow.
     const int resident_warps = min_ctas * c.sm_count * warps;
+    // Split passes of the slab driver.  The edge launch (subset 1) runs the first and last two
+    // EDGE_H-row segments of the owned range: they produce every row a neighbour's halo needs, also
+    // of the restricted grid (8 coarse rows <= 22 fine rows up to ratio 2.5; the last segment may be
+    // ragged, hence two).  The interior launch (subset 2) is an ordinary launch over the rest.
+    constexpr int EDGE_H = 24, EDGE_E = 2;
+    if (p.subset != 0) {
+        const int n_edge_segs = (p.own_hi - p.own_lo + EDGE_H - 1) / EDGE_H;
+        if (n_edge_segs < 2 * EDGE_E + 1) {         // too thin to split: the edge launch does it all
+            if (p.subset == 2) return;
+            p.subset = 0;
+        } else if (p.subset == 2) {
+            p.own_hi = p.own_lo + EDGE_H * (n_edge_segs - EDGE_E);
+            p.own_lo += EDGE_H * EDGE_E;
+            p.subset = 0;                            // (err_add stays set)
+        }
+    }
     const int own_rows = p.own_hi - p.own_lo;
     int H = g_force_H;
-    if (H <= 0) {
+    if (p.subset == 1) H = EDGE_H;
+    else if (H <= 0) {
         const long long row_strips = (long long)own_rows * p.n_strips;
         H = (int)(row_strips / (4LL * resident_warps));
         H = std::max(32, std::min(256, H));
-        if ((long long)((own_rows + H - 1) / H) * p.n_strips < resident_warps) H = std::max(16, (int)(row_strips / resident_warps));
         H = std::min(256, (H + 7) / 8 * 8);
+        if ((long long)((own_rows + H - 1) / H) * p.n_strips < resident_warps) {
+            // Small grid: fewer tasks than resident warps, so a lone warp's latency is the pass time
+            // (about 1 us per row, measured).  Take the segment height that minimises
+            // rounds x (rows + warm-up rows + fixed cost) over 4..32.
+            long long best = -1;
+            for (int h = 4; h <= 32; ++h) {
+                const long long tasks = (long long)((own_rows + h - 1) / h) * p.n_strips;
+                const long long rounds = (tasks + resident_warps - 1) / resident_warps;
+                const long long cost = rounds * (h + lead_rows + 6);
+                if (best < 0 || cost <= best) { best = cost; H = h; }
+            }
+        }
     }
     p.H = H;
     p.n_segs = (own_rows + H - 1) / H;
-    p.n_tasks = p.n_strips * p.n_segs;
+    p.edge_E = EDGE_E;
+    p.n_tasks = p.n_strips * (p.subset == 1 ? 2 * EDGE_E : p.n_segs);
+    if (p.n_tasks == 0) return;
     // the kernel indexes every grid with GLOBAL rows: shift the bases of the local arrays
     p.F_valid = p.F;
     const ptrdiff_t fine_shift = (ptrdiff_t)p.row0 * N;
@@ -123,13 +154,14 @@ void launch_stream(StreamParams &p)
         constexpr int IN4 = IN == IN_PROLONG ? IN_LOAD : IN;
         using G4 = Stream4Geo<S, ERR || RES, RES>;
         static bool opted4 = false;
-        launch_stream_kernel(k_stream4<S, IN4, ERR, RES>, p, G4::W, S4_WARPS, S4_MIN_CTAS, stream4_smem_bytes(), ERR, opted4);
+        launch_stream_kernel(k_stream4<S, IN4, ERR, RES>, p, G4::W, S4_WARPS, S4_MIN_CTAS, stream4_smem_bytes(), ERR, 2 * S + 3, opted4);
         return;
     }
     using G = StreamGeo<S, ERR || RES, RES>;
     constexpr int STREAM_WARPS = stream_shape(RES).warps, STREAM_MIN_CTAS = stream_shape(RES).min_ctas;
     static bool opted_in = false;   // one flag per instantiation
-    launch_stream_kernel(k_stream<S, IN, ERR, RES>, p, G::W, STREAM_WARPS, STREAM_MIN_CTAS, stream_smem_bytes(IN, STREAM_WARPS), ERR, opted_in);
+    launch_stream_kernel(k_stream<S, IN, ERR, RES>, p, G::W, STREAM_WARPS, STREAM_MIN_CTAS, stream_smem_bytes(IN, STREAM_WARPS), ERR, 2 * S + 3,
+                         opted_in);
 }
 
 template <int IN, bool ERR, bool RES>
@@ -276,7 +308,7 @@ int restrict_first_coarse_at_or_after(int N, int M, int fine_row)
 
 void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
                bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
-               const Slab *coarse_in)
+               const Slab *coarse_in, int subset)
 {
     const Spacing sp = spacing(N, L);
     StreamParams p{};
@@ -286,6 +318,8 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
     p.own_lo = fine.own_lo;
     p.own_hi = fine.own_hi;
     p.raw_sum = 1;
+    p.subset = subset;
+    p.err_add = subset == 2 ? 1 : 0;             // the interior launch adds to the edge launch's sum
     p.h2 = sp.h2;
     p.inv_h2 = sp.inv_h2;
     p.F = F;

@@ -38,6 +38,9 @@ int restrict_first_coarse_at_or_after(int N, int M, int fine_row);
 // the negated residual into the local F_c array of that coarse slab.  coarse_in: the local U_c.
 void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
                bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
-               const Slab *coarse_in);
+               const Slab *coarse_in, int subset = 0);
+// subset: 0 the whole slab; 1 only thin row segments at both ends of the owned range (they produce
+// every row the neighbours' halos need); 2 the interior in between (its error sum is ADDED to the
+// edge launch's).  1 followed by 2 is equivalent to 0.
 
 }  // namespace mg

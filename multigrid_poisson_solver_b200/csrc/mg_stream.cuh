@@ -79,8 +79,10 @@ struct StreamParams {
     int fc_row0;            // global index of local row 0 of the F_c array
     int uc_row0, uc_rows;   // global index of local row 0 of the U_c array, and its local row count
     int raw_sum;            // ERR: write the plain red-parity sum (the host combines slabs) instead of (S+S)/N/N
+    int subset, edge_E;     // 0: all row segments; 1: only the edge_E first + last ones (edge launch of a split pass)
+    int err_add;            // ERR: add this launch's sum to *err_dev (the other part of a split pass wrote it)
     int H;                  // rows owned by one task
-    int n_strips, n_segs, n_tasks;   // tasks (strip, row segment) are handed to warps through an atomic queue
+    int n_strips, n_segs, n_tasks;   // tasks (strip, row segment of the chosen subset) are handed to warps through an atomic queue
     double h2, inv_h2;
     const double *F_valid;  // any dereferenceable address (source operand of zero-fill copies)
     const double *Uin;      // IN_LOAD: U ; IN_PROLONG: U_f
@@ -244,8 +246,10 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     if (lane == 0) task = (int)atomicAdd(p.counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.n_tasks) break;
-    const int seg = task / p.n_strips;
-    const int strip = task - seg * p.n_strips;            // consecutive tasks = adjacent strips of one row segment
+    const int seg_idx = task / p.n_strips;
+    const int strip = task - seg_idx * p.n_strips;
+    // edge launch of a split pass (multi-GPU overlap): only the edge_E first and last row segments
+    const int seg = p.subset == 1 ? (seg_idx < p.edge_E ? seg_idx : p.n_segs - 2 * p.edge_E + seg_idx) : seg_idx;            // consecutive tasks = adjacent strips of one row segment
     constexpr bool active = true;
 
     const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
@@ -562,6 +566,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
         if (lane == 0) {
             double e = s;
+            if (p.err_add && p.err_dev) e = __dadd_rn(*p.err_dev, s);   // second launch of a split pass
             if (!p.raw_sum) {
                 e = __dadd_rn(s, s);                              // sum1 + sum2 over the same parity (:621)
                 e = __ddiv_rn(e, (double)N);

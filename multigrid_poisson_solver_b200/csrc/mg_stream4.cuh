@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(S4_WARPS * 32, S4_MIN_CTAS) k_stream4(const St
     if (lane == 0) task = (int)atomicAdd(p.counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.n_tasks) break;
-    const int seg = task / p.n_strips;
-    const int strip = task - seg * p.n_strips;
+    const int seg_idx = task / p.n_strips;
+    const int strip = task - seg_idx * p.n_strips;
+    // edge launch of a split pass (multi-GPU overlap): only the edge_E first and last row segments
+    const int seg = p.subset == 1 ? (seg_idx < p.edge_E ? seg_idx : p.n_segs - 2 * p.edge_E + seg_idx) : seg_idx;
 
     const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
     const int c_first = own_c_lo - G::HL;                           // first column of the 128-wide window (multiple of 4)
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(S4_WARPS * 32, S4_MIN_CTAS) k_stream4(const St
         for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
         if (lane == 0) {
             double e = s;
+            if (p.err_add && p.err_dev) e = __dadd_rn(*p.err_dev, s);   // second launch of a split pass
             if (!p.raw_sum) {
                 e = __dadd_rn(s, s);
                 e = __ddiv_rn(e, (double)N);
