@@ -102,10 +102,14 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
     int H = g_force_H;
     if (p.subset == 1) H = EDGE_H;
     else if (H <= 0) {
+        // Rows per task.  Measured on B200 for every pass type and N = 2048..16384: the best height
+        // follows H ~ 3.5 sqrt(x), x = rows per resident warp -- the optimum of
+        // x (1 + warm-up/H) [redundant rows] + c H [tail: warps finish up to a task apart].
         const long long row_strips = (long long)own_rows * p.n_strips;
-        H = (int)(row_strips / (4LL * resident_warps));
-        H = std::max(32, std::min(256, H));
-        H = std::min(256, (H + 7) / 8 * 8);
+        const double x = (double)row_strips / (double)resident_warps;
+        H = (int)(3.5 * std::sqrt(x) + 0.5);
+        H = H >= 32 ? (H + 4) / 8 * 8 : (H + 2) / 4 * 4;
+        H = std::max(8, std::min(256, H));
         if ((long long)((own_rows + H - 1) / H) * p.n_strips < resident_warps) {
             // Small grid: fewer tasks than resident warps, so a lone warp's latency is the pass time
             // (about 1 us per row, measured).  Take the segment height that minimises
