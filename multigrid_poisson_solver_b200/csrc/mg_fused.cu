@@ -5,6 +5,7 @@
 #include "mg_fused.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -68,6 +69,93 @@ const FusedRestrictTable &fused_restrict_table(int N, int M)
     return g_restrict_tables.emplace(std::make_pair(N, M), t).first->second;
 }
 
+// ---- row segments of a pass (one task = one strip x one segment)
+// Measured on B200 for every pass type, N = 2048..16384, uniform height H: the time behaves like
+// x (1 + warm-up/H) + c H with x = rows per resident warp -- redundant warm-up rows against a tail
+// in which warps finish up to one task apart (best uniform H ~ 3.5 sqrt(x)).  The table therefore
+// hands out tall segments first and shrinks them towards the end of the queue (guided
+// self-scheduling): height = remaining work / (g x resident warps), clamped to [h_min, h_max].
+// Grids with fewer tasks than resident warps are latency bound instead (a lone warp needs about
+// 1 us per row): they get the uniform height that minimises rounds x (rows + warm-up + fixed cost).
+// Split passes of the slab driver: the edge launch (subset 1) runs two EDGE_H-row segments at each
+// end of the owned range -- they produce every row a neighbour's halo needs, also of the restricted
+// grid (8 coarse rows <= 22 fine rows up to ratio 2.5; the last segment may be ragged, hence two) --
+// and the interior launch (subset 2) the rows in between.
+struct SegmentTable {
+    int2 *dev = nullptr;
+    int n = 0;
+};
+int g_sched_hmax = 256, g_sched_hmin = 16;
+double g_sched_g = 1.5;
+
+std::vector<int2> build_segments(int rows, int n_strips, int resident_warps, int lead_rows, int subset)
+{
+    constexpr int EDGE_H = 24, EDGE_E = 2;
+    std::vector<int2> out;
+    int lo = 0, hi = rows;
+    if (subset != 0) {
+        const int n_edge = (rows + EDGE_H - 1) / EDGE_H;
+        if (n_edge < 2 * EDGE_E + 1) {               // too thin to split: the edge launch does it all
+            if (subset == 2) return out;
+        } else if (subset == 1) {
+            for (int k = 0; k < EDGE_E; ++k) out.push_back(make_int2(k * EDGE_H, (k + 1) * EDGE_H));
+            for (int k = n_edge - EDGE_E; k < n_edge; ++k) out.push_back(make_int2(k * EDGE_H, std::min(rows, (k + 1) * EDGE_H)));
+            return out;
+        } else {
+            lo = EDGE_H * EDGE_E;
+            hi = EDGE_H * (n_edge - EDGE_E);
+        }
+    }
+    const int span = hi - lo;
+    auto uniform = [&](int H) {
+        for (int r = lo; r < hi; r += H) out.push_back(make_int2(r, std::min(hi, r + H)));
+    };
+    if (g_force_H > 0) { uniform(g_force_H); return out; }
+    const double x = (double)span * n_strips / (double)resident_warps;
+    int H = (int)(3.5 * std::sqrt(x) + 0.5);
+    H = std::max(8, std::min(256, H >= 32 ? (H + 4) / 8 * 8 : (H + 2) / 4 * 4));
+    if ((long long)((span + H - 1) / H) * n_strips < resident_warps) {      // latency-bound small grid
+        long long best = -1;
+        for (int h = 4; h <= 32; ++h) {
+            const long long tasks = (long long)((span + h - 1) / h) * n_strips;
+            const long long rounds = (tasks + resident_warps - 1) / resident_warps;
+            const long long cost = rounds * (h + lead_rows + 6);
+            if (best < 0 || cost <= best) { best = cost; H = h; }
+        }
+        uniform(H);
+        return out;
+    }
+    if (g_sched_g <= 0.0) { uniform(H); return out; }
+    int r = lo;
+    while (r < hi) {
+        const int left = hi - r;
+        int h = (int)((double)left * n_strips / (g_sched_g * resident_warps));
+        h = std::max(g_sched_hmin, std::min(g_sched_hmax, h / 4 * 4));
+        if (left - h < g_sched_hmin / 2) h = left;   // no sliver at the end
+        h = std::min(h, left);
+        out.push_back(make_int2(r, r + h));
+        r += h;
+    }
+    return out;
+}
+
+const SegmentTable &segment_table(int rows, int n_strips, int resident_warps, int lead_rows, int subset)
+{
+    static std::map<std::vector<int>, SegmentTable> cache;
+    const std::vector<int> key = {rows, n_strips, resident_warps, lead_rows, subset};
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    SegmentTable t;
+    const std::vector<int2> segs = build_segments(rows, n_strips, resident_warps, lead_rows, subset);
+    t.n = (int)segs.size();
+    if (t.n > 0) {
+        bool ok = check(cudaMalloc(&t.dev, segs.size() * sizeof(int2)), "cudaMalloc segment table");
+        ok = ok && check(cudaMemcpy(t.dev, segs.data(), segs.size() * sizeof(int2), cudaMemcpyHostToDevice), "H2D segment table");
+        if (!ok) t.n = 0;
+    }
+    return cache.emplace(key, t).first->second;
+}
+
 int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
 
 // Task geometry, persistent grid and launch shared by the two streaming kernels.
@@ -78,56 +166,12 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
     Context &c = ctx();
     const int N = p.N;
     p.n_strips = (N + W - 1) / W;
-    // Rows per task: about four tasks per resident warp when the grid is large enough (halo rows
-    // cost (2S+3)/H of extra work, so at least 32 rows), otherwise as many tasks as 16-row
-    // segments allow.
     const int resident_warps = min_ctas * c.sm_count * warps;
-    // Split passes of the slab driver.  The edge launch (subset 1) runs the first and last two
-    // EDGE_H-row segments of the owned range: they produce every row a neighbour's halo needs, also
-    // of the restricted grid (8 coarse rows <= 22 fine rows up to ratio 2.5; the last segment may be
-    // ragged, hence two).  The interior launch (subset 2) is an ordinary launch over the rest.
-    constexpr int EDGE_H = 24, EDGE_E = 2;
-    if (p.subset != 0) {
-        const int n_edge_segs = (p.own_hi - p.own_lo + EDGE_H - 1) / EDGE_H;
-        if (n_edge_segs < 2 * EDGE_E + 1) {         // too thin to split: the edge launch does it all
-            if (p.subset == 2) return;
-            p.subset = 0;
-        } else if (p.subset == 2) {
-            p.own_hi = p.own_lo + EDGE_H * (n_edge_segs - EDGE_E);
-            p.own_lo += EDGE_H * EDGE_E;
-            p.subset = 0;                            // (err_add stays set)
-        }
-    }
-    const int own_rows = p.own_hi - p.own_lo;
-    int H = g_force_H;
-    if (p.subset == 1) H = EDGE_H;
-    else if (H <= 0) {
-        // Rows per task.  Measured on B200 for every pass type and N = 2048..16384: the best height
-        // follows H ~ 3.5 sqrt(x), x = rows per resident warp -- the optimum of
-        // x (1 + warm-up/H) [redundant rows] + c H [tail: warps finish up to a task apart].
-        const long long row_strips = (long long)own_rows * p.n_strips;
-        const double x = (double)row_strips / (double)resident_warps;
-        H = (int)(3.5 * std::sqrt(x) + 0.5);
-        H = H >= 32 ? (H + 4) / 8 * 8 : (H + 2) / 4 * 4;
-        H = std::max(8, std::min(256, H));
-        if ((long long)((own_rows + H - 1) / H) * p.n_strips < resident_warps) {
-            // Small grid: fewer tasks than resident warps, so a lone warp's latency is the pass time
-            // (about 1 us per row, measured).  Take the segment height that minimises
-            // rounds x (rows + warm-up rows + fixed cost) over 4..32.
-            long long best = -1;
-            for (int h = 4; h <= 32; ++h) {
-                const long long tasks = (long long)((own_rows + h - 1) / h) * p.n_strips;
-                const long long rounds = (tasks + resident_warps - 1) / resident_warps;
-                const long long cost = rounds * (h + lead_rows + 6);
-                if (best < 0 || cost <= best) { best = cost; H = h; }
-            }
-        }
-    }
-    p.H = H;
-    p.n_segs = (own_rows + H - 1) / H;
-    p.edge_E = EDGE_E;
-    p.n_tasks = p.n_strips * (p.subset == 1 ? 2 * EDGE_E : p.n_segs);
-    if (p.n_tasks == 0) return;
+    const SegmentTable &st = segment_table(p.own_hi - p.own_lo, p.n_strips, resident_warps, lead_rows, p.subset);
+    if (st.n == 0) return;                           // (an interior launch with nothing left to do)
+    p.segs = st.dev;
+    p.n_segs = st.n;
+    p.n_tasks = p.n_strips * p.n_segs;
     // the kernel indexes every grid with GLOBAL rows: shift the bases of the local arrays
     p.F_valid = p.F;
     const ptrdiff_t fine_shift = (ptrdiff_t)p.row0 * N;
@@ -143,9 +187,23 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
         check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(k_stream)");
         opted_in = true;
     }
+    static const char *trace_path = getenv("MG_TASK_TRACE");       // debug: dump the task time line of every launch
+    if (trace_path) check(cudaMalloc(&p.trace, (size_t)(4 * p.n_tasks + 1) * sizeof(unsigned long long)), "cudaMalloc trace");
     kernel<<<blocks, warps * 32, smem_bytes, c.stream>>>(p);
     c.launches++;
     check(cudaGetLastError(), "k_stream");
+    if (trace_path && p.trace) {
+        std::vector<unsigned long long> h((size_t)4 * p.n_tasks + 1);
+        cudaStreamSynchronize(c.stream);
+        cudaMemcpy(h.data(), p.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaFree(p.trace);
+        if (FILE *f = fopen(trace_path, "a")) {
+            fprintf(f, "launch N=%d strips=%d segs=%d tasks=%d warps=%d end=%llu\n", N, p.n_strips, p.n_segs, p.n_tasks, blocks * warps, h.back());
+            for (int t = 0; t < p.n_tasks; ++t)
+                fprintf(f, "%d %llu %llu %llu %llu\n", t, h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+            fclose(f);
+        }
+    }
 }
 
 template <int S, int IN, bool ERR, bool RES>
@@ -361,6 +419,9 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
 void fused_init()
 {
     if (const char *h = getenv("MG_STREAM_H")) g_force_H = atoi(h);
+    if (const char *h = getenv("MG_SCHED_HMAX")) g_sched_hmax = std::max(4, atoi(h));
+    if (const char *h = getenv("MG_SCHED_HMIN")) g_sched_hmin = std::max(4, atoi(h));
+    if (const char *h = getenv("MG_SCHED_G")) g_sched_g = atof(h);     // <= 0: uniform segments
     if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
     if (const char *d = getenv("MG_COLS4")) g_cols4 = atoi(d);
 }

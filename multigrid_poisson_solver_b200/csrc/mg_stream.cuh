@@ -79,9 +79,10 @@ struct StreamParams {
     int fc_row0;            // global index of local row 0 of the F_c array
     int uc_row0, uc_rows;   // global index of local row 0 of the U_c array, and its local row count
     int raw_sum;            // ERR: write the plain red-parity sum (the host combines slabs) instead of (S+S)/N/N
-    int subset, edge_E;     // 0: all row segments; 1: only the edge_E first + last ones (edge launch of a split pass)
+    int subset;             // host only: 0 whole owned range; 1 / 2 edge / interior launch of a split pass (slab driver)
     int err_add;            // ERR: add this launch's sum to *err_dev (the other part of a split pass wrote it)
-    int H;                  // rows owned by one task
+    unsigned long long *trace;   // debug (MG_TASK_TRACE): per task {start ns, end ns, SM, warp}; nullptr normally
+    const int2 *segs;       // [n_segs] row segments {first, past-last}, relative to own_lo; one task = (strip, segment)
     int n_strips, n_segs, n_tasks;   // tasks (strip, row segment of the chosen subset) are handed to warps through an atomic queue
     double h2, inv_h2;
     const double *F_valid;  // any dereferenceable address (source operand of zero-fill copies)
@@ -141,6 +142,15 @@ __device__ __forceinline__ bool div_unsafe(double x)
 {
     const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
     return e - 200u > 1600u;                       // zero, subnormal, huge, inf, nan
+}
+// Guard for TWO chained divisions (x / d) / d with 2^-20 <= d <= 1: if x passes, so does the first
+// quotient (its exponent grows by at most 20), so one test covers both.  +0 passes too -- div_fast
+// maps it to +0 exactly, and it is what every boundary column and off-grid lane feeds in (flagging
+// it made the two edge strips of every row segment take the IEEE path on every row).
+__device__ __forceinline__ bool div2_unsafe(double x)
+{
+    const unsigned hi = (unsigned)__double2hiint(x), e = (hi >> 20) & 0x7ffu;
+    return (e - 220u > 1560u) && ((hi | (unsigned)__double2loint(x)) != 0u);
 }
 
 // s4 - 4*u with one rounding == the reference's (s4 - RN(4*u)) because 4*u is exact.
@@ -246,10 +256,11 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     if (lane == 0) task = (int)atomicAdd(p.counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.n_tasks) break;
+    unsigned long long trace_t0 = 0;
+    if (p.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
     const int seg_idx = task / p.n_strips;
     const int strip = task - seg_idx * p.n_strips;
-    // edge launch of a split pass (multi-GPU overlap): only the edge_E first and last row segments
-    const int seg = p.subset == 1 ? (seg_idx < p.edge_E ? seg_idx : p.n_segs - 2 * p.edge_E + seg_idx) : seg_idx;            // consecutive tasks = adjacent strips of one row segment
+    const int seg = seg_idx;                                    // consecutive tasks = adjacent strips of one row segment
     constexpr bool active = true;
 
     const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
@@ -260,7 +271,8 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     const bool x_in = cx > 0, y_in = cx + 1 < N - 1;            // interior columns
     const bool strip_fast = c_first >= 1 && c_first + 63 <= N - 2;   // every column of the window is interior
     // all row indices below are GLOBAL; the arrays are addressed with (row - row0)
-    const int own_r_lo = p.own_lo + seg * p.H, own_r_hi = min(own_r_lo + p.H, p.own_hi);
+    const int2 seg_rows = __ldg(p.segs + seg);                  // rows of the segment relative to own_lo
+    const int own_r_lo = p.own_lo + seg_rows.x, own_r_hi = p.own_lo + seg_rows.y;
     const int r_first = max(0, own_r_lo - G::ROW_LEAD);
     const int r_last = min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD);
 
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         x_next.x = __dadd_rn(uf.x, div_fast(qx, d, y));
         x_next.y = __dadd_rn(uf.y, div_fast(qy, d, y));
         pvx = vx; pvy = vy; puf_x = uf.x; puf_y = uf.y;
-        return div_unsafe(vx) | div_unsafe(qx) | div_unsafe(vy) | div_unsafe(qy);
+        return col_ok && (div2_unsafe(vx) | div2_unsafe(vy));    // off-grid lanes compute -0 = c * 0 (never stored)
     };
     auto prolong_redo = [&](bool bad) {                          // rare: IEEE divisions for the whole warp
         if (__any_sync(0xffffffffu, bad)) {
@@ -548,6 +560,16 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
         if (lane == 0) p.partials[task] = v;
     }
+    if (p.trace && lane == 0) {
+        unsigned long long t1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[4 * task + 0] = trace_t0;
+        p.trace[4 * task + 1] = t1;
+        p.trace[4 * task + 2] = smid;
+        p.trace[4 * task + 3] = blockIdx.x * STREAM_WARPS + warp;
+    }
   }  // task loop
 
     // ---- the last warp to finish resets the queue and folds the per-task partials in task order
@@ -561,7 +583,13 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     __threadfence();
     if (ERR) {
         double s = 0.0;
-        for (int k = lane; k < p.n_tasks; k += 32) s = __dadd_rn(s, __ldcg(&p.partials[k]));
+        for (int k0 = lane; k0 < p.n_tasks; k0 += 32 * 8) {      // eight loads in flight, then added in task order
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = k0 + 32 * j < p.n_tasks ? __ldcg(&p.partials[k0 + 32 * j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = __dadd_rn(s, v[j]);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
         if (lane == 0) {
@@ -579,6 +607,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     if (lane == 0) {
         p.counter[0] = 0u;
         p.counter[1] = 0u;
+        if (p.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.trace[4 * p.n_tasks]));   // after the fold
     }
 }
 

@@ -73,8 +73,7 @@ __global__ void __launch_bounds__(S4_WARPS * 32, S4_MIN_CTAS) k_stream4(const St
     if (task >= p.n_tasks) break;
     const int seg_idx = task / p.n_strips;
     const int strip = task - seg_idx * p.n_strips;
-    // edge launch of a split pass (multi-GPU overlap): only the edge_E first and last row segments
-    const int seg = p.subset == 1 ? (seg_idx < p.edge_E ? seg_idx : p.n_segs - 2 * p.edge_E + seg_idx) : seg_idx;
+    const int seg = seg_idx;                                    // consecutive tasks = adjacent strips of one row segment
 
     const int own_c_lo = strip * G::W, own_c_hi = min(own_c_lo + G::W, N);
     const int c_first = own_c_lo - G::HL;                           // first column of the 128-wide window (multiple of 4)
@@ -88,7 +87,8 @@ __global__ void __launch_bounds__(S4_WARPS * 32, S4_MIN_CTAS) k_stream4(const St
     const bool own01 = ok_col[0] && cx >= own_c_lo && cx < own_c_hi;            // ownership per 16-byte pair
     const bool own23 = ok_col[2] && cx + 2 >= own_c_lo && cx + 2 < own_c_hi;
     const bool strip_fast = c_first >= 1 && c_first + 127 <= N - 2;
-    const int own_r_lo = p.own_lo + seg * p.H, own_r_hi = min(own_r_lo + p.H, p.own_hi);
+    const int2 seg_rows = __ldg(p.segs + seg);                  // rows of the segment relative to own_lo
+    const int own_r_lo = p.own_lo + seg_rows.x, own_r_hi = p.own_lo + seg_rows.y;
     const int r_first = max(0, own_r_lo - G::ROW_LEAD);
     const int r_last = min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD);
 
@@ -281,7 +281,13 @@ __global__ void __launch_bounds__(S4_WARPS * 32, S4_MIN_CTAS) k_stream4(const St
     __threadfence();
     if (ERR) {
         double s = 0.0;
-        for (int k = lane; k < p.n_tasks; k += 32) s = __dadd_rn(s, __ldcg(&p.partials[k]));
+        for (int k0 = lane; k0 < p.n_tasks; k0 += 32 * 8) {      // eight loads in flight, then added in task order
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = k0 + 32 * j < p.n_tasks ? __ldcg(&p.partials[k0 + 32 * j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = __dadd_rn(s, v[j]);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
         if (lane == 0) {
