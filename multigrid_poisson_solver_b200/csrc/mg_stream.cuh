@@ -153,6 +153,59 @@ __device__ __forceinline__ bool div2_unsafe(double x)
     return (e - 220u > 1560u) && ((hi | (unsigned)__double2loint(x)) != 0u);
 }
 
+// ---- end of a launch: the last CTA to drain the queue resets it and folds the per-task error
+// partials.  Thread t adds partials t, t+T, ... in that order, then the fixed shuffle tree and the
+// warps in order: the summation tree depends only on the task geometry and the CTA shape, never on
+// which warp ran which task.  A whole CTA keeps 16 loads per thread in flight (a lone warp needed
+// ~1 us per 1024 partials: 14-20 us of tail at N >= 8192).
+template <int WARPS, bool ERR>
+__device__ __forceinline__ void finish_launch(const StreamParams &p)
+{
+    __shared__ double fold_s[WARPS];
+    __shared__ unsigned int fold_last;
+    constexpr int T = WARPS * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) __threadfence();               // this warp's partials, before the CTA's ticket
+    __syncthreads();                              // every warp of this CTA has drained the queue
+    if (tid == 0) fold_last = atomicAdd(p.counter + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!fold_last) return;
+    __threadfence();
+    if (ERR) {
+        double s = 0.0;
+        for (int k0 = tid; k0 < p.n_tasks; k0 += T * 16) {
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = k0 + T * j < p.n_tasks ? __ldcg(&p.partials[k0 + T * j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s = __dadd_rn(s, v[j]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+        if (lane == 0) fold_s[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            s = fold_s[0];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) s = __dadd_rn(s, fold_s[w]);
+            double e = s;
+            if (p.err_add && p.err_dev) e = __dadd_rn(*p.err_dev, s);   // second launch of a split pass
+            if (!p.raw_sum) {
+                e = __dadd_rn(s, s);                              // sum1 + sum2 over the same parity (:621)
+                e = __ddiv_rn(e, (double)p.N);
+                e = __ddiv_rn(e, (double)p.N);
+            }
+            if (p.err_dev) *p.err_dev = e;
+            if (p.err_slot) *p.err_slot = e;                      // host-mapped; the host reads it after a stream sync
+        }
+    }
+    if (tid == 0) {
+        p.counter[0] = 0u;
+        p.counter[1] = 0u;
+        if (p.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.trace[4 * p.n_tasks]));   // after the fold
+    }
+}
+
 // s4 - 4*u with one rounding == the reference's (s4 - RN(4*u)) because 4*u is exact.
 __device__ __forceinline__ double sub4(double s4, double u) { return __fma_rn(-4.0, u, s4); }
 
@@ -572,43 +625,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     }
   }  // task loop
 
-    // ---- the last warp to finish resets the queue and folds the per-task partials in task order
-    unsigned int done = 0;
-    if (lane == 0) {
-        __threadfence();
-        done = atomicAdd(p.counter + 1, 1u);
-    }
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != gridDim.x * STREAM_WARPS - 1) return;
-    __threadfence();
-    if (ERR) {
-        double s = 0.0;
-        for (int k0 = lane; k0 < p.n_tasks; k0 += 32 * 8) {      // eight loads in flight, then added in task order
-            double v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = k0 + 32 * j < p.n_tasks ? __ldcg(&p.partials[k0 + 32 * j]) : 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s = __dadd_rn(s, v[j]);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-        if (lane == 0) {
-            double e = s;
-            if (p.err_add && p.err_dev) e = __dadd_rn(*p.err_dev, s);   // second launch of a split pass
-            if (!p.raw_sum) {
-                e = __dadd_rn(s, s);                              // sum1 + sum2 over the same parity (:621)
-                e = __ddiv_rn(e, (double)N);
-                e = __ddiv_rn(e, (double)N);
-            }
-            if (p.err_dev) *p.err_dev = e;
-            if (p.err_slot) { *p.err_slot = e; __threadfence_system(); }
-        }
-    }
-    if (lane == 0) {
-        p.counter[0] = 0u;
-        p.counter[1] = 0u;
-        if (p.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.trace[4 * p.n_tasks]));   // after the fold
-    }
+    finish_launch<STREAM_WARPS, ERR>(p);
 }
 
 }  // namespace mg

@@ -271,41 +271,7 @@ __global__ void __launch_bounds__(S4_WARPS * 32, S4_MIN_CTAS) k_stream4(const St
     }
   }  // task loop
 
-    unsigned int done = 0;
-    if (lane == 0) {
-        __threadfence();
-        done = atomicAdd(p.counter + 1, 1u);
-    }
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != gridDim.x * S4_WARPS - 1) return;
-    __threadfence();
-    if (ERR) {
-        double s = 0.0;
-        for (int k0 = lane; k0 < p.n_tasks; k0 += 32 * 8) {      // eight loads in flight, then added in task order
-            double v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = k0 + 32 * j < p.n_tasks ? __ldcg(&p.partials[k0 + 32 * j]) : 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s = __dadd_rn(s, v[j]);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-        if (lane == 0) {
-            double e = s;
-            if (p.err_add && p.err_dev) e = __dadd_rn(*p.err_dev, s);   // second launch of a split pass
-            if (!p.raw_sum) {
-                e = __dadd_rn(s, s);
-                e = __ddiv_rn(e, (double)N);
-                e = __ddiv_rn(e, (double)N);
-            }
-            if (p.err_dev) *p.err_dev = e;
-            if (p.err_slot) { *p.err_slot = e; __threadfence_system(); }
-        }
-    }
-    if (lane == 0) {
-        p.counter[0] = 0u;
-        p.counter[1] = 0u;
-    }
+    finish_launch<S4_WARPS, ERR>(p);
 }
 
 }  // namespace mg
