@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--steps", type=int, nargs="*", default=[3])
+    ap.add_argument("--warm", type=int, default=3, help="untimed calls per leg (0 for a profiler capture)")
     a = ap.parse_args()
     lib = mg.init(0)
     stream = torch.cuda.ExternalStream(lib.mgStream(), device=0)
@@ -29,7 +30,7 @@ def main():
     slot = lib.mgScalarSlot(100)
 
     def timeit(fn):
-        for _ in range(3):
+        for _ in range(a.warm):
             fn()
         lib.mgSync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
