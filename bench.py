@@ -48,14 +48,49 @@ def write_cycle(text):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """SM clock + throttle reasons sampled every ~2 ms WHILE the timed region runs (NVML from a
+    thread: the timed loop sits in ctypes calls, which release the GIL).  nvidia-smi -lms is the
+    fallback when NVML cannot be loaded; it needs ~100 ms to start, so short regions may get no sample."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.path = gpu, None, None
+        self.nvml, self.handle, self.thread, self.stop = None, None, None, False
+        self.samples, self.max_mhz = [], None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(gpu)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv, h = self.nvml, self.handle
+        while not self.stop:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        if self.nvml:
+            import threading
+            self.stop = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return self
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -67,6 +102,9 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.thread:
+            self.stop = True
+            self.thread.join(timeout=2)
         if self.proc:
             time.sleep(0.05)
             self.proc.terminate()
@@ -77,6 +115,15 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.nvml:
+            if self.samples:
+                bits = 0
+                for _, r in self.samples:
+                    bits |= r
+                out = {"sm_mhz": statistics.median(s for s, _ in self.samples), "sm_max_mhz": self.max_mhz,
+                       "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(self.samples),
+                       "source": "NVML, every ~2 ms inside the timed region"}
+            return out
         if not self.path or not os.path.exists(self.path):
             return out
         sm, mx, reasons = [], [], set()
@@ -97,6 +144,7 @@ class ClockSampler:
             out["sm_mhz"] = statistics.median(sm)
             out["sm_max_mhz"] = max(mx)
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi -lms 20 inside the timed region"
         out["reasons"] = sorted(reasons)
         return out
 
@@ -219,12 +267,13 @@ def main():
             raise SystemExit("mgRunCycleFile failed: %d %s" % (rc, lib.mgLastError().decode()))
         return res.launches, res.time_ms
 
+    clk = ClockSampler(local)                       # NVML set up before the warm-up, sampling only inside the timed region
     for _ in range(args.warmup):
         one_cycle()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, inner_ms = 0, 0.0
-    with ClockSampler(local) as clk:
+    with clk:
         ev0.record(stream)
         for _ in range(args.steps):
             l, t = one_cycle()
@@ -242,33 +291,54 @@ def main():
     check = mg.run_cycle(path, base_flags & ~mg.RUN_NO_FINAL_ERROR)
     mg_error = check["mg_error"]
 
-    # ---- end to end through the host-buffer ABI call ---------------------------------------
+    # ---- end to end through the host-buffer ABI calls -----------------------------------------
+    # Headline: mgRunCycleFileHostBatch, one problem per step -- every step copies its source from
+    # pinned host memory to the device, runs the V-cycle and reads the solution back into pinned
+    # host memory; consecutive steps are double-buffered (upload i+1 / cycle i / download i-1).
+    # `single_call`: the same through one mgRunCycleFileHost call per step (no overlap at all).
     e2e = None
     if not args.no_e2e:
-        hF = torch.empty(n, dtype=torch.float64).pin_memory()
-        hU = torch.empty(n, dtype=torch.float64).pin_memory()
-        lib.mgGridDownload(N, F.ptr, hF.data_ptr())
-        e2e_steps = max(2, min(args.steps, 5))
+        import ctypes as C
+        hF = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+        hU = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+        for h in hF:
+            lib.mgGridDownload(N, F.ptr, h.data_ptr())
 
-        def one_e2e():
-            rc = lib.mgRunCycleFileHost(os.fsencode(path), base_flags, hF.data_ptr(), hU.data_ptr(), recs, 64, res)
+        def timed(fn, steps):
+            fn(2)                                   # warm-up (also first-touch of the staging grids)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            t0 = time.perf_counter()
+            fn(steps)
+            e1.record(stream)
+            barrier()
+            wall = time.perf_counter() - t0
+            return max_over_ranks(max(e0.elapsed_time(e1), 1000.0 * wall)) / steps
+
+        def single(k):
+            for i in range(k):
+                rc = lib.mgRunCycleFileHost(os.fsencode(path), base_flags, hF[i % 2].data_ptr(), hU[i % 2].data_ptr(), recs, 64, res)
+                if rc != 0:
+                    raise SystemExit("mgRunCycleFileHost failed: %d" % rc)
+
+        def batch(k):
+            Fp, Up, rs = (C.c_void_p * k)(), (C.c_void_p * k)(), (api.CycleResult * k)()
+            for i in range(k):
+                Fp[i], Up[i] = hF[i % 2].data_ptr(), hU[i % 2].data_ptr()
+            rc = lib.mgRunCycleFileHostBatch(os.fsencode(path), base_flags, k, Fp, Up, rs)
             if rc != 0:
-                raise SystemExit("mgRunCycleFileHost failed: %d" % rc)
+                raise SystemExit("mgRunCycleFileHostBatch failed: %d" % rc)
 
-        one_e2e()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            one_e2e()
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1000.0 * wall)) / e2e_steps
+        single_ms = timed(single, max(2, min(args.steps, 3)))
+        e2e_steps = max(2, min(args.steps, 10))
+        e2e_ms = timed(batch, e2e_steps)
         e2e = {"value": world * 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "call": "mgRunCycleFileHost(cycle file, pinned F_host -> device, V-cycle, U -> pinned U_host)"}
+               "call": "mgRunCycleFileHostBatch(cycle file, one problem per step: pinned F_host -> device, V-cycle, U -> pinned "
+                       "U_host; upload of step i+1 and download of step i-1 overlap the cycle of step i)",
+               "single_call": {"value": world * 1000.0 / single_ms, "ms_per_step": single_ms,
+                               "call": "mgRunCycleFileHost per step (upload, V-cycle, download strictly in sequence)"}}
         del hF, hU
 
     # ---- roofline of the dominant kernel, timed alone on the library's stream -----------------
@@ -338,12 +408,13 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
             raise SystemExit("mgDistRunCycleFile failed: %d %s" % (rc, lib.mgLastError().decode()))
         return res.launches
 
+    clk = ClockSampler(local)
     for _ in range(max(args.warmup, 1)):
         one_cycle()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    with ClockSampler(local) as clk:
+    with clk:
         ev0.record(stream)
         for _ in range(args.steps):
             launches += one_cycle()

@@ -162,6 +162,13 @@ void mgSubcycleHarvest(void);
  * copied to the device, the cycle runs, the solution is copied back into U_host. */
 int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double *U_host,
                        mgTraceRec *recs, int max_recs, mgCycleResult *res);
+/* n independent problems through the same cycle file, HOST buffers (pinned for full speed),
+ * double-buffered: upload of problem i+1 and download of problem i-1 overlap the cycle of problem i.
+ * F_hosts[i] / U_hosts[i]: N_max^2 doubles each, all non-NULL; res: n results or NULL.
+ * Bit-identical to n mgRunCycleFileHost calls (which is what the reference's main() would do per problem,
+ * MG_solver_CPU.cpp:149-462). */
+int mgRunCycleFileHostBatch(const char *path, int flags, int n, const double *const *F_hosts, double *const *U_hosts,
+                            mgCycleResult *res);
 
 /* ------------------------------------------------------------ multi-GPU (row slabs)
  * One process per GPU.  Levels with at least `threshold` rows are partitioned into row slabs

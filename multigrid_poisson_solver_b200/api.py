@@ -69,6 +69,7 @@ ABI = {
                                 C.POINTER(TraceRec), C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgSubcycleHarvest": (None, []),
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
+    "mgRunCycleFileHostBatch": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),
     "mgDistPlan": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgDistUniqueId": (C.c_int, [_vp]),
@@ -297,6 +298,40 @@ def run_cycle_host(path, flags=RUN_FUSED | RUN_QUIET, F_host=None, want_U=True, 
         assert F_host.size == N * N
         Fp = F_host.ctypes.data
     return _run("mgRunCycleFileHost", path, flags, Fp, N if want_U else 0, max_recs)
+
+
+def run_cycle_host_batch(path, F_hosts, flags=RUN_FUSED | RUN_QUIET, U_ptrs=None):
+    """mgRunCycleFileHostBatch: independent problems (one host source each) through the same cycle
+    file; uploads, cycles and downloads of consecutive problems overlap.  F_hosts: arrays or raw
+    host pointers (ints, e.g. of pinned torch tensors); U_ptrs: raw host pointers to fill, else
+    numpy arrays are allocated and returned."""
+    l = _need()
+    N = _n_max(path)
+    n = len(F_hosts)
+    keep, Fp = [], (C.c_void_p * n)()
+    for i, F in enumerate(F_hosts):
+        if isinstance(F, int):
+            Fp[i] = F
+        else:
+            a = np.ascontiguousarray(F, dtype=np.float64).reshape(-1)
+            assert a.size == N * N
+            keep.append(a)
+            Fp[i] = a.ctypes.data
+    Up, Us = (C.c_void_p * n)(), None
+    if U_ptrs is None:
+        Us = [np.empty(N * N) for _ in range(n)]
+        for i, U in enumerate(Us):
+            Up[i] = U.ctypes.data
+    else:
+        for i, u in enumerate(U_ptrs):
+            Up[i] = u
+    res = (CycleResult * n)()
+    rc = l.mgRunCycleFileHostBatch(os.fsencode(path), flags, n, Fp, Up, res)
+    if rc != 0:
+        msg = l.mgLastError().decode()
+        l.mgClearError()
+        raise MGLibraryError("mgRunCycleFileHostBatch(%s) failed with code %d %s" % (path, rc, msg))
+    return dict(U=Us, mg_error=[r.mg_error for r in res], time_ms=[r.time_ms for r in res], launches=[r.launches for r in res])
 
 
 def run_cycle(path, flags=RUN_FUSED | RUN_QUIET, max_recs=8192):

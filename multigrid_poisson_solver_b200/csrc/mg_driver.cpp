@@ -576,3 +576,57 @@ extern "C" int mgRunCycleFileHost(const char *path, int flags, const double *F_h
     mgGridFree(dU);
     return rc;
 }
+
+// n independent problems (same cycle file, different sources) with HOST buffers, double-buffered:
+// while the cycle of problem i runs, the source of problem i+1 is uploaded and the solution of
+// problem i-1 is downloaded on two copy streams (PCIe is full duplex, and a 2 GiB copy takes ten
+// times longer than the cycle at N = 16384).  Results are bit-identical to n mgRunCycleFileHost calls.
+extern "C" int mgRunCycleFileHostBatch(const char *path, int flags, int n, const double *const *F_hosts, double *const *U_hosts,
+                                       mgCycleResult *res)
+{
+    if (mgLastErrorCode()) return 10;
+    if (n < 1 || !F_hosts || !U_hosts) return 11;
+    for (int i = 0; i < n; ++i)
+        if (!F_hosts[i] || !U_hosts[i]) return 11;
+    std::ifstream f(path);
+    if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
+    double L, mx, my; int cs, cn, N_max, N_min;
+    f >> L >> mx >> my >> cs >> cn >> N_max >> N_min;
+    if (!f) return 2;
+    f.close();
+    const size_t bytes = (size_t)N_max * N_max * sizeof(double);
+    cudaStream_t compute = (cudaStream_t)mgStream(), up = nullptr, down = nullptr;
+    cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
+    double *dF[2] = {mgGridAlloc(N_max), n > 1 ? mgGridAlloc(N_max) : nullptr};
+    double *dU[2] = {mgGridAlloc(N_max), n > 1 ? mgGridAlloc(N_max) : nullptr};
+    std::vector<cudaEvent_t> uploaded((size_t)n), downloaded((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&downloaded[i], cudaEventDisableTiming);
+    }
+    int rc = (dF[0] && dU[0] && (n == 1 || (dF[1] && dU[1]))) ? 0 : 12;
+    auto upload = [&](int i) {      // the previous reader of dF[i % 2], cycle i-2, has been waited for on the host
+        cudaMemcpyAsync(dF[i % 2], F_hosts[i], bytes, cudaMemcpyHostToDevice, up);
+        cudaEventRecord(uploaded[i], up);
+    };
+    mgSync();                       // the staging grids may be recycled blocks with work still queued on them
+    if (rc == 0) upload(0);
+    for (int i = 0; i < n && rc == 0; ++i) {
+        if (i + 1 < n) upload(i + 1);
+        cudaStreamWaitEvent(compute, uploaded[i], 0);
+        if (i >= 2) cudaStreamWaitEvent(compute, downloaded[i - 2], 0);      // dU[i % 2] is free again
+        rc = run(path, flags | MG_RUN_SKIP_SOURCE, dF[i % 2], dU[i % 2], nullptr, 0, res ? res + i : nullptr);   // returns synchronised
+        if (rc) break;
+        cudaMemcpyAsync(U_hosts[i], dU[i % 2], bytes, cudaMemcpyDeviceToHost, down);
+        cudaEventRecord(downloaded[i], down);
+    }
+    cudaStreamSynchronize(up);
+    cudaStreamSynchronize(down);
+    if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = 13;
+    for (int i = 0; i < n; ++i) { cudaEventDestroy(uploaded[i]); cudaEventDestroy(downloaded[i]); }
+    cudaStreamDestroy(up);
+    cudaStreamDestroy(down);
+    for (int k = 0; k < 2; ++k) { mgGridFree(dF[k]); mgGridFree(dU[k]); }
+    return rc;
+}

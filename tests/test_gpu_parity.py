@@ -252,6 +252,23 @@ def test_cycle_against_reference_golden(name, mode, goldens, golden_dir, orc):
     assert_same(r["U"], ref_U, "final U of %s (%s)" % (name, mode))
 
 
+@pytest.mark.parametrize("name,n", [("Vcycle", 1), ("Vcycle", 5), ("Wcycle", 3), ("VcycleTrigger", 2)])
+def test_host_batch_equals_single_calls(name, n, golden_dir, orc):
+    """mgRunCycleFileHostBatch (double-buffered uploads / cycles / downloads) returns, problem by
+    problem, the bits of mgRunCycleFileHost -- different sources so that a mixed-up buffer shows."""
+    import multigrid_poisson_solver_b200 as mg
+    path = os.path.join(golden_dir, "cycle_%s.txt" % name)
+    L, mx, my, N = header(path)
+    F0 = orc.getSource(N, L, mx, my)
+    Fs = [F0 * (1.0 + 0.25 * k) for k in range(n)]
+    flags = mg.RUN_FUSED | mg.RUN_QUIET
+    batch = mg.run_cycle_host_batch(path, Fs, flags)
+    for k in range(n):
+        one = mg.run_cycle_host(path, flags, F_host=Fs[k])
+        assert_same(batch["U"][k], one["U"], "problem %d of %d (%s)" % (k, n, name))
+        assert batch["mg_error"][k] == one["mg_error"]
+
+
 @pytest.mark.parametrize("name", ["Vcycle", "Wcycle", "VcycleTrigger"])
 def test_cycle_with_device_source(name, goldens, golden_dir):
     """End to end with getSource on the device: U within 1e-12 relative of the reference."""
