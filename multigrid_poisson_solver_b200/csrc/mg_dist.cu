@@ -2,15 +2,16 @@
 //
 // Fine levels are partitioned into contiguous row slabs, one per rank (one process per GPU);
 // every slab carries HALO extra rows on each side.  A fused pass needs the halo rows of its
-// input to be current, so the protocol per node is
-//     -1 node : [exchange U halos unless U = 0]  pass(es)  ->  F_c rows  ->  exchange F_c halos
-//      1 node : exchange U_f and U_c halos       pass(es)
-// with one exchange between two passes of the same node (step > 3).  The coarse partition is
-// INDUCED by the fine one through the reference's floor map (a rank owns the coarse rows whose
-// lower fine row it owns), so restriction needs no communication at all and prolongation only
-// the coarse halo.  Levels below `threshold` rows are agglomerated on rank 0 (gather of F_c on
-// the way down, scatter of U_c with halos on the way up); the other ranks idle there.
-// The smoothing error is the all-reduced sum of the slabs' red-parity sums.
+// input to be current; they are refreshed WHEN AN ARRAY IS PRODUCED: right behind every pass one
+// grouped send/recv carries the edge rows of its output (and of the restricted F_c) to both
+// neighbours, so no pass exchanges before it reads and a node costs one communication group.
+// The coarse partition is INDUCED by the fine one through the reference's floor map (a rank owns
+// the coarse rows whose lower fine row it owns), so restriction needs no communication at all and
+// prolongation only the coarse halo.  Levels below `threshold` rows are agglomerated on rank 0
+// (gather of F_c on the way down, scatter of U_c with halos on the way up) and handed as one
+// sub-cycle to the single-GPU interpreter; the other ranks idle there.
+// The smoothing error is the all-reduced sum of the slabs' red-parity sums (one collective per
+// batch of nodes; per sweep only in the trigger mode).
 //
 // Two communicators implement the same three primitives (point-to-point row transfers, scalar
 // all-reduce):
