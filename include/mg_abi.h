@@ -36,6 +36,11 @@ void mgClearError(void);
 void mgSync(void);                      /* wait for everything queued so far */
 void *mgStream(void);                   /* the context's cudaStream_t (for event timing by callers) */
 int mgKernelLaunches(void);             /* kernels launched by this library since mgInit */
+/* Task geometry of a fused pass (host-only, no GPU needed): the row segments {first, past-last},
+ * relative to the first owned row, in the order the persistent warps take them.  subset: 0 the
+ * whole owned range, 1 / 2 the edge / interior launch of a split slab pass.  Returns the number
+ * of segments written to out[2*k], out[2*k+1], or < 0. */
+int mgSegmentPlan(int rows, int n_strips, int resident_warps, int lead_rows, int subset, int *out, int max_out);
 
 double *mgGridAlloc(int N);             /* pooled device array of N*N doubles (uninitialised, like malloc) */
 void mgGridFree(double *grid);

@@ -71,6 +71,7 @@ ABI = {
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgRunCycleFileHostBatch": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),
+    "mgSegmentPlan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgDistPlan": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgDistUniqueId": (C.c_int, [_vp]),
     "mgDistInit": (C.c_int, [C.c_int, C.c_int, _vp]),
@@ -390,6 +391,16 @@ def run_cycle_dist(path, threshold, flags=RUN_FUSED | RUN_QUIET, want_U=False, m
     if want_U:
         out["U_own"] = U[: (hi.value - lo.value) * N].copy()
     return out
+
+
+def segment_plan(rows, n_strips, resident_warps, lead_rows=9, subset=0):
+    """Row segments [(first, past_last), ...] of a fused pass in queue order (host-only)."""
+    l = lib()
+    out = (C.c_int * (2 * rows + 2))()
+    n = l.mgSegmentPlan(rows, n_strips, resident_warps, lead_rows, subset, out, len(out))
+    if n < 0:
+        raise MGLibraryError("mgSegmentPlan failed with code %d" % n)
+    return [(out[2 * k], out[2 * k + 1]) for k in range(n)]
 
 
 def dist_plan(ladder, world, threshold):

@@ -187,6 +187,16 @@ void mgShutdown(void)
     c = Context();
 }
 
+int mgSegmentPlan(int rows, int n_strips, int resident_warps, int lead_rows, int subset, int *out, int max_out)
+{
+    // host-only: usable without a GPU (tests of the task geometry)
+    if (rows < 1 || n_strips < 1 || resident_warps < 1 || lead_rows < 0 || subset < 0 || subset > 2) return -1;
+    const std::vector<int> plan = segment_plan(rows, n_strips, resident_warps, lead_rows, subset);
+    if ((int)plan.size() > max_out) return -2;
+    for (size_t i = 0; i < plan.size(); ++i) out[i] = plan[i];
+    return (int)plan.size() / 2;
+}
+
 int mgLastErrorCode(void) { return ctx().err_code; }
 const char *mgLastError(void) { return ctx().err_msg.c_str(); }
 void mgClearError(void) { ctx().err_code = 0; ctx().err_msg.clear(); }

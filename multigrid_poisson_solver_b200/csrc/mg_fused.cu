@@ -354,6 +354,14 @@ double *run_leg(int N, double L, const double *in, double *a, double *b, const d
 
 }  // namespace
 
+std::vector<int> segment_plan(int rows, int n_strips, int resident_warps, int lead_rows, int subset)
+{
+    std::vector<int> out;
+    for (const int2 &sg : build_segments(rows, n_strips, resident_warps, lead_rows, subset)) { out.push_back(sg.x); out.push_back(sg.y); }
+    return out;
+}
+
+
 // ------------------------------------------------------------------ row-slab passes (multi-GPU)
 bool slab_pair_fusable(int N, int M)
 {

@@ -1,5 +1,6 @@
 // mg_fused.h -- smoothing passes and the fused cycle legs (internal C++ API).
 #pragma once
+#include <vector>
 #include "mg_context.h"
 
 namespace mg {
@@ -42,5 +43,9 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
 // subset: 0 the whole slab; 1 only thin row segments at both ends of the owned range (they produce
 // every row the neighbours' halos need); 2 the interior in between (its error sum is ADDED to the
 // edge launch's).  1 followed by 2 is equivalent to 0.
+
+// Row segments {first, past-last} (relative to the first owned row) a fused pass over `rows` owned rows
+// hands to its warps, in queue order; host-only (no device state).  subset as in slab_pass.
+std::vector<int> segment_plan(int rows, int n_strips, int resident_warps, int lead_rows, int subset);
 
 }  // namespace mg

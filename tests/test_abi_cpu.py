@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import multigrid_poisson_solver_b200 as mg
@@ -90,3 +91,52 @@ def test_ladders():
     assert cycles.ladder(40, 33, con_N=2) == list(range(40, 32, -1))
     w = cycles.tokens(cycles.w_cycle(64, 8))
     assert w.count(0.0) >= 4    # 2^(levels-1) exact solves (+ the 0.0 origin fields)
+
+
+# ----------------------------------------------------------------------------- task geometry (host-only)
+P_RES, P_PLAIN = 148 * 2 * 8, 148 * 3 * 4      # resident warps of the two CTA shapes (mg_stream.cuh)
+
+
+@pytest.mark.parametrize("rows,n_strips,warps", [
+    (16384, 293, P_PLAIN), (16384, 304, P_RES), (8192, 147, P_PLAIN), (11584, 414, P_RES), (5792, 828, P_RES),
+    (4096, 74, P_PLAIN), (2048, 37, P_RES), (1024, 19, P_PLAIN), (256, 5, P_PLAIN), (64, 2, P_RES), (7, 1, P_RES),
+    (65536, 1171, P_PLAIN), (1447, 52, P_PLAIN)])
+def test_segment_plan_partitions_the_owned_rows(rows, n_strips, warps):
+    """The row segments of a fused pass tile [0, rows) exactly once, in order, without empty ones;
+    large grids get tall segments first and short ones last (no tail), small grids uniform ones."""
+    import multigrid_poisson_solver_b200 as mg
+    segs = mg.api.segment_plan(rows, n_strips, warps, 9, 0)
+    assert segs[0][0] == 0 and segs[-1][1] == rows
+    for (a, b), (c, d) in zip(segs, segs[1:]):
+        assert a < b and b == c
+    heights = [b - a for a, b in segs]
+    assert max(heights) <= 256
+    assert len(segs) <= 16384
+    if len(segs) * n_strips >= 4 * warps:                      # throughput regime: guided schedule
+        assert heights[0] == max(heights)
+        assert all(h1 >= h2 for h1, h2 in zip(heights[:-2], heights[1:-1]))   # non-increasing (last one may absorb a sliver)
+        assert heights[-1] <= max(32, heights[0] // 4)
+    # deterministic: the plan is a pure function of its arguments
+    assert segs == mg.api.segment_plan(rows, n_strips, warps, 9, 0)
+
+
+@pytest.mark.parametrize("rows", [40, 97, 120, 121, 500, 5792, 11584, 16384])
+def test_split_pass_edge_plus_interior_is_the_whole_pass(rows):
+    """Slab passes launched in two parts (mg_dist.cu, MG_DIST_OVERLAP): the edge launch and the
+    interior launch together cover every owned row exactly once, and the edge launch alone holds
+    the first and last 24 rows -- all a neighbour's halo (8 rows, <= 22 fine rows for the
+    restricted grid) can need."""
+    import multigrid_poisson_solver_b200 as mg
+    edge = mg.api.segment_plan(rows, 100, P_RES, 9, 1)
+    inner = mg.api.segment_plan(rows, 100, P_RES, 9, 2)
+    cover = np.zeros(rows, dtype=int)
+    for a, b in edge + inner:
+        assert 0 <= a < b <= rows
+        cover[a:b] += 1
+    assert np.all(cover == 1)
+    in_edge = np.zeros(rows, dtype=bool)
+    for a, b in edge:
+        in_edge[a:b] = True
+    assert np.all(in_edge[:min(24, rows)]) and np.all(in_edge[max(0, rows - 24):])
+    if rows >= 24 * 5:
+        assert len(edge) == 4 and inner

@@ -73,6 +73,25 @@ def test_non_power_of_two_ladder(mg):
     compare(mg, mg.cycles.v_cycle(1448, 8), 4, 300)        # 1448 -> 724 -> 362 -> 181 (odd, agglomerated)
 
 
+@pytest.fixture
+def overlapped(monkeypatch):
+    """MG_DIST_OVERLAP=1: passes launched as edge + interior, communication on its own stream."""
+    monkeypatch.setenv("MG_DIST_OVERLAP", "1")
+    yield
+    monkeypatch.delenv("MG_DIST_OVERLAP", raising=False)
+
+
+@pytest.mark.parametrize("text,world,threshold", [
+    ("v1024", 2, 256), ("v1024", 8, 256), ("w512", 4, 128), ("trigger512", 4, 128), ("step5", 3, 128), ("restart", 4, 128),
+    ("v4096", 4, 1024)])
+def test_overlapped_exchange_matches_single_gpu(mg, overlapped, text, world, threshold):
+    """The split-launch / two-stream protocol must give the same bits as the in-line one."""
+    texts = {"v1024": mg.cycles.v_cycle(1024, 8), "w512": mg.cycles.w_cycle(512, 8, levels=4, step=2, tol=1e-7),
+             "trigger512": mg.cycles.v_cycle(512, 8, step=-1), "step5": mg.cycles.v_cycle(512, 16, step=5),
+             "restart": mg.cycles.v_cycle(512, 8, step=2, cycles=2), "v4096": mg.cycles.v_cycle(4096, 8)}
+    compare(mg, texts[text], world, threshold)
+
+
 def test_large_grid_slabs(mg):
     compare(mg, mg.cycles.v_cycle(4096, 8), 8, 1024)
 
