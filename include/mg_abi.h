@@ -41,6 +41,12 @@ int mgKernelLaunches(void);             /* kernels launched by this library sinc
  * whole owned range, 1 / 2 the edge / interior launch of a split slab pass.  Returns the number
  * of segments written to out[2*k], out[2*k+1], or < 0. */
 int mgSegmentPlan(int rows, int n_strips, int resident_warps, int lead_rows, int subset, int *out, int max_out);
+/* Which whole grids the shared-memory tile kernel serves instead of the streaming kernel.  Default
+ * (n < 0): odd sizes up to 1024 -- the streaming kernel needs even N and is as fast on small even
+ * grids.  n >= 0: every size up to n (0: never); also MG_TILE_MAX_N.  Returns the old setting (-1 =
+ * default).  All paths produce the same bits; the switch exists for tuning and for testing each
+ * kernel on every size. */
+int mgSetTileMaxN(int n);
 
 double *mgGridAlloc(int N);             /* pooled device array of N*N doubles (uninitialised, like malloc) */
 void mgGridFree(double *grid);

@@ -71,6 +71,7 @@ ABI = {
     "mgRunCycleFileHost": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgRunCycleFileHostBatch": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(CycleResult)]),
     "mgPrint2File": (C.c_int, [C.c_int, _vp, C.c_char_p]),
+    "mgSetTileMaxN": (C.c_int, [C.c_int]),
     "mgSegmentPlan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgDistPlan": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mgDistUniqueId": (C.c_int, [_vp]),

@@ -187,6 +187,8 @@ void mgShutdown(void)
     c = Context();
 }
 
+int mgSetTileMaxN(int n) { return set_tile_max_n(n); }
+
 int mgSegmentPlan(int rows, int n_strips, int resident_warps, int lead_rows, int subset, int *out, int max_out)
 {
     // host-only: usable without a GPU (tests of the task geometry)

@@ -12,6 +12,7 @@
 #include "mg_kernels.h"
 #include "mg_stream.cuh"
 #include "mg_stream4.cuh"
+#include "mg_tile.cuh"
 
 namespace mg {
 namespace {
@@ -156,6 +157,11 @@ const SegmentTable &segment_table(int rows, int n_strips, int resident_warps, in
     return cache.emplace(key, t).first->second;
 }
 
+// Whole grids up to g_tile_max_N take the shared-memory tile kernel (mg_tile.cuh): by default only ODD sizes (the
+// streaming kernel needs even N and is as fast on small even grids: 14 us per node either way at N = 256, measured);
+// MG_TILE_MAX_N / mgSetTileMaxN(n >= 0) route every size up to n through it (0 disables it).
+int g_tile_max_N = 1024;
+bool g_tile_even = false;
 int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
 
 // Task geometry, persistent grid and launch shared by the two streaming kernels.
@@ -206,9 +212,31 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
     }
 }
 
+// Small whole grids: one CTA per 32 x 32 tile instead of one warp per strip (mg_tile.cuh).
+bool tile_ok(const StreamParams &p)
+{
+    return g_tile_max_N > 0 && p.N <= g_tile_max_N && (g_tile_even || p.N % 2 != 0) && p.row0 == 0 && p.rows == p.N && p.own_lo == 0 && p.own_hi == p.N &&
+           !p.raw_sum && !p.subset && !p.err_add;
+}
+
+template <int S, int IN, bool ERR, bool RES>
+void launch_tile(StreamParams &p)
+{
+    Context &c = ctx();
+    const int tiles = (p.N + TILE - 1) / TILE, blocks = tiles * tiles;
+    if (ERR) {
+        p.partials = partials_buf((size_t)blocks);
+        p.counter = c.counters + 10;   // last-CTA ticket (self-resetting)
+    }
+    k_tile<S, IN, ERR, RES><<<blocks, TILE_THREADS, 0, c.stream>>>(p);
+    c.launches++;
+    check(cudaGetLastError(), "k_tile");
+}
+
 template <int S, int IN, bool ERR, bool RES>
 void launch_stream(StreamParams &p)
 {
+    if (tile_ok(p)) { launch_tile<S, IN, ERR, RES>(p); return; }
     // Measured on B200 (N = 16384): 4 columns per lane win for the passes without restriction (smoothing
     // pass 1.05 vs 1.09 ms); with restriction the 230-254 registers leave 8 warps per SM and lose (1.40 vs 1.22 ms).
     if (IN != IN_PROLONG && !RES && g_cols4) {
@@ -255,6 +283,8 @@ void launch_stream_any(int S, int in, int mode, StreamParams &p)
 }
 
 bool streamable(int N) { return !g_disable && N >= 4 && (N % 2 == 0); }
+// a whole grid the fused passes can serve: even (streaming kernel) or small (tile kernel, any parity)
+bool fusable(int N) { return !g_disable && N >= 4 && (N % 2 == 0 || N <= g_tile_max_N); }
 
 // Split `step` sweeps into passes of at most STREAM_SMAX, as evenly as possible.
 std::vector<int> split_passes(int step)
@@ -432,12 +462,21 @@ void fused_init()
     if (const char *h = getenv("MG_SCHED_G")) g_sched_g = atof(h);     // <= 0: uniform segments
     if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
     if (const char *d = getenv("MG_COLS4")) g_cols4 = atoi(d);
+    if (const char *d = getenv("MG_TILE_MAX_N")) { g_tile_max_N = std::max(0, atoi(d)); g_tile_even = true; }
+}
+
+int set_tile_max_n(int n)
+{
+    const int old = g_tile_even ? g_tile_max_N : -1;
+    if (n >= 0) { g_tile_max_N = n; g_tile_even = true; }      // every size up to n (0: never)
+    else        { g_tile_max_N = 1024; g_tile_even = false; }   // default: odd sizes up to 1024
+    return old;
 }
 
 int smooth_pass_count(int N, int step)
 {
     if (step <= 0) return 0;
-    return streamable(N) ? (step + STREAM_SMAX - 1) / STREAM_SMAX : step;
+    return fusable(N) ? (step + STREAM_SMAX - 1) / STREAM_SMAX : step;
 }
 
 double *smooth_out_of_place(int N, double L, const double *in, double *a, double *b, const double *F, int step,
@@ -449,7 +488,7 @@ double *smooth_out_of_place(int N, double L, const double *in, double *a, double
         in = a;
         std::swap(a, b);
     }
-    if (streamable(N) && (step > 0 || want_err)) {
+    if (fusable(N) && (step > 0 || want_err)) {
         LegSpec spec;
         spec.in = (in_is_zero && step > 0) ? IN_ZERO : IN_LOAD;
         spec.want_err = want_err;
@@ -472,7 +511,7 @@ double *smooth_out_of_place(int N, double L, const double *in, double *a, double
 double *down_leg(int N, double L, double *U, double *U_work, const double *F, int step, bool zero_init, int M,
                  double *F_c, double *err_slot)
 {
-    if (streamable(N) && fused_restrict_table(N, M).usable) {
+    if (fusable(N) && fused_restrict_table(N, M).usable) {
         if (step == 0 && zero_init) check(cudaMemsetAsync(U, 0, (size_t)N * N * sizeof(double), ctx().stream), "cudaMemsetAsync");
         LegSpec spec;
         spec.in = (zero_init && step > 0) ? IN_ZERO : IN_LOAD;
@@ -499,7 +538,7 @@ double *up_leg(int Nc, const double *U_c, int N, double L, double *U_f, double *
                double *err_slot)
 {
     // a 64-column window must map into at most 62 coarse cells (the staged part of a coarse row)
-    if (streamable(N) && Nc >= 2 && (double)(N - 1) >= 1.2 * (double)(Nc - 1)) {
+    if (fusable(N) && Nc >= 2 && (double)(N - 1) >= 1.2 * (double)(Nc - 1)) {
         LegSpec spec;
         spec.in = IN_PROLONG;
         spec.Nc = Nc;

@@ -6,6 +6,7 @@
 namespace mg {
 
 void fused_init();
+int set_tile_max_n(int n);   // n >= 0: whole grids up to n take the tile kernel (0: never); n < 0: default (odd sizes up to 1024); returns the old setting
 
 // `step` Jacobi sweeps (MG_solver_CPU.cpp:578-601) followed by the smoothing error (:607-622).
 // The first pass reads `in` (never written; treated as all zeros when in_is_zero) and the

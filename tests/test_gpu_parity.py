@@ -32,6 +32,19 @@ def orc():
     return po.oracle_ops()
 
 
+@pytest.fixture(autouse=True, params=["tile", "stream"])
+def fused_kernel(request):
+    """Every test runs twice: with every whole grid up to N = 1024 routed through the
+    shared-memory tile kernel, and with that kernel switched off, so that the streaming kernel
+    (even N) or the one-kernel-per-operator path (odd N) serves the same sizes.  All three must
+    give the same bits.  (Default outside the tests: tile kernel for odd sizes only.)"""
+    import multigrid_poisson_solver_b200 as mg
+    lib = mg.init(0)
+    lib.mgSetTileMaxN(1024 if request.param == "tile" else 0)
+    yield request.param
+    lib.mgSetTileMaxN(-1)
+
+
 def grids(N, seed, zero_boundary=False):
     rng = np.random.default_rng(seed)
     U = rng.random(N * N) - 0.25
