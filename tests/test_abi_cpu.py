@@ -140,3 +140,25 @@ def test_split_pass_edge_plus_interior_is_the_whole_pass(rows):
     assert np.all(in_edge[:min(24, rows)]) and np.all(in_edge[max(0, rows - 24):])
     if rows >= 24 * 5:
         assert len(edge) == 4 and inner
+
+
+# ----------------------------------------------------------------------------- bench contract (CPU arm)
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU implementation timed on the host) prints
+    ONE JSON line with the keys of the bench contract; bounded sample so that it runs in a second."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--ref-sample", "128",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("V-cycles/sec") and d["unit"] == "V-cycles/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
