@@ -375,8 +375,6 @@ public:
     TwoStream ts;
     int scal_used_ = 0;         // slots of the ranks' scal arrays holding error sums of this batch
 
-    bool want_dist(int N) const { return comm.world > 1 && N >= threshold_; }
-
     void push(const LevelGeom &g, double *borrowed_F = nullptr)
     {
         geom.push_back(g);
@@ -422,8 +420,6 @@ public:
             return nullptr;
         }, xs);
     }
-
-    void zero(double *p, const Slab &s, int N) { check(cudaMemsetAsync(p, 0, (size_t)s.rows * N * sizeof(double), ts.ms), "memset"); }
 
     // sum the ranks' partials at scal[idx .. idx+n); every local rank ends with the global sums (on ts.cs)
     void allreduce(int idx, int n = 1)
@@ -591,8 +587,6 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     const std::vector<const double *> no_uc;
     const std::vector<Slab> no_slab;
 
-    // one node's smoothing on a distributed level: `step` sweeps (or the trigger loop), optional
-    // restriction into the next level; returns sweeps done and records the error
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
