@@ -162,3 +162,25 @@ def test_reference_arm_prints_the_contract_line():
         assert key in d, key
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_segment_plan_properties_random():
+    """Property check over random shapes (hypothesis): whatever the grid, strip count and CTA shape,
+    the segments tile the owned rows exactly once and the split launches add up to the whole pass."""
+    from hypothesis import given, settings, strategies as st
+    import multigrid_poisson_solver_b200 as mg
+
+    @settings(max_examples=300, deadline=None)
+    @given(rows=st.integers(1, 70000), n_strips=st.integers(1, 1200), warps=st.sampled_from([P_RES, P_PLAIN, 148 * 2 * 4]),
+           lead=st.integers(3, 11))
+    def check(rows, n_strips, warps, lead):
+        whole = mg.api.segment_plan(rows, n_strips, warps, lead, 0)
+        assert whole[0][0] == 0 and whole[-1][1] == rows
+        assert all(a < b for a, b in whole) and all(x[1] == y[0] for x, y in zip(whole, whole[1:]))
+        assert max(b - a for a, b in whole) <= 256 and len(whole) <= 16384
+        cover = np.zeros(rows, dtype=np.int8)
+        for a, b in mg.api.segment_plan(rows, n_strips, warps, lead, 1) + mg.api.segment_plan(rows, n_strips, warps, lead, 2):
+            cover[a:b] += 1
+        assert np.all(cover == 1)
+
+    check()
