@@ -13,6 +13,11 @@
 // The smoothing error is the all-reduced sum of the slabs' red-parity sums (one collective per
 // batch of nodes; per sweep only in the trigger mode).
 //
+// Transports of the row transfers: NCCL send/recv groups (default), or -- MG_DIST_TRANSPORT=staged --
+// copy engines writing into fixed staging buffers of the destination rank (opened once through CUDA
+// IPC) with sequence flags handled by stream memory operations: no SM is needed, so the exchange
+// really overlaps a persistent compute kernel (StagedTransport below).
+//
 // Two communicators implement the same three primitives (point-to-point row transfers, scalar
 // all-reduce):
 //   EmuComm   all ranks live in this process on the current GPU (device-to-device copies).  It
@@ -20,6 +25,7 @@
 //   NcclComm  one rank per process; ncclSend/ncclRecv groups and ncclAllReduce on the library's
 //             stream.  NCCL is bound at run time (dlopen of the libnccl.so.2 the host program --
 //             e.g. torch -- already loaded), so the library has no link-time NCCL dependency.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -64,11 +70,181 @@ public:
     virtual void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) = 0;
 };
 
+
+// ------------------------------------------------------------------ staged peer-to-peer transport
+// Row transfers without communication kernels.  Every rank owns a staging area with one slot per
+// (source rank, message parity) and a few 32-bit words: flag[src] (sequence number of the last
+// message src has delivered here), ack[dst] (last message of mine dst has consumed).  A message
+// from s to d is
+//     s:  wait  ack[d] >= seq - 2            (the slot of this parity is free again)
+//         copy  rows -> d.stage[s][seq & 1]   (peer write by a copy engine, over NVLink)
+//         write d.flag[s] = seq               (4-byte copy behind the data, same stream: ordered)
+//     d:  wait  flag[s] >= seq                (stream memory operation: no SM, no host)
+//         copy  stage[s][seq & 1] -> rows     (local)
+//         write s.ack[d] = seq
+// Sequence numbers are counted per ordered pair on both sides; every rank walks the same transfer
+// lists in the same order, so they agree without any handshake.  All sends of a call are queued
+// before its receives, hence no cycle of waits.  The staging areas of the other ranks are mapped
+// once (CUDA IPC when they live in other processes).
+struct DriverApi {
+    CUresult (*WaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    CUresult (*WriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    bool load()
+    {
+        if (WaitValue32 && WriteValue32) return true;
+        cudaDriverEntryPointQueryResult q;
+        void *f = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return false;
+        WaitValue32 = (decltype(WaitValue32))f;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return false;
+        WriteValue32 = (decltype(WriteValue32))f;
+        return true;
+    }
+};
+DriverApi g_drv;
+
+class StagedTransport {
+public:
+    static constexpr size_t CAP = 8u << 20;      // bytes per (source rank, parity) slot
+    struct Local {                                // one per rank living in this process
+        int rank = -1;
+        unsigned char *stage = nullptr;           // [world][2][CAP]
+        unsigned int *words = nullptr;            // flag[world] | ack[world] | scratch[2]
+        std::vector<unsigned char *> peer_stage;  // every rank's staging area as seen from here
+        std::vector<unsigned int *> peer_words;
+        std::vector<unsigned int> seq_out, seq_in;
+    };
+    int world = 0;
+    std::vector<Local> locals;
+    bool ready = false;
+
+    ~StagedTransport()
+    {
+        for (Local &l : locals) {
+            for (int q = 0; q < world; ++q) {
+                if (q == l.rank || ipc_opened.empty()) continue;
+                if (ipc_opened[q]) { cudaIpcCloseMemHandle(l.peer_stage[q]); cudaIpcCloseMemHandle(l.peer_words[q]); }
+            }
+            cudaFree(l.stage);
+            cudaFree(l.words);
+        }
+    }
+    std::vector<char> ipc_opened;                 // per rank: its areas were opened through IPC (one local rank only)
+
+    size_t words_count() const { return (size_t)2 * world + 2; }
+    bool add_local(int rank, int world_)
+    {
+        world = world_;
+        Local l;
+        l.rank = rank;
+        if (cudaMalloc(&l.stage, (size_t)world * 2 * CAP) != cudaSuccess) return false;
+        if (cudaMalloc(&l.words, words_count() * sizeof(unsigned int)) != cudaSuccess) return false;
+        if (cudaMemset(l.words, 0, words_count() * sizeof(unsigned int)) != cudaSuccess) return false;
+        l.peer_stage.assign((size_t)world, nullptr);
+        l.peer_words.assign((size_t)world, nullptr);
+        l.seq_out.assign((size_t)world, 0u);
+        l.seq_in.assign((size_t)world, 0u);
+        locals.push_back(l);
+        return true;
+    }
+    // all ranks in this process: the "peer" views are the other ranks' own pointers
+    bool link_in_process()
+    {
+        for (Local &a : locals)
+            for (Local &b : locals) { a.peer_stage[b.rank] = b.stage; a.peer_words[b.rank] = b.words; }
+        ready = g_drv.load();
+        return ready;
+    }
+    Local *local_of(int rank)
+    {
+        for (Local &l : locals) if (l.rank == rank) return &l;
+        return nullptr;
+    }
+    // same answer on every rank: it depends on the transfer sizes only
+    bool applicable(const std::vector<Xfer> &xs) const
+    {
+        if (!ready) return false;
+        std::map<std::pair<int, int>, size_t> bytes;
+        for (const Xfer &x : xs)
+            if (x.count && x.src_rank != x.dst_rank) bytes[{x.src_rank, x.dst_rank}] += x.count * sizeof(double);
+        for (const auto &kv : bytes) if (kv.second > CAP) return false;
+        return true;
+    }
+    void wait32(cudaStream_t st, unsigned int *addr, unsigned int value)
+    {
+        if (g_drv.WaitValue32((CUstream)st, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) fail(-36, "cuStreamWaitValue32");
+    }
+    // *remote = value, ordered behind everything queued on st so far (local scratch word, then a 4-byte copy)
+    void post32(cudaStream_t st, Local &l, int scratch, unsigned int *remote, unsigned int value)
+    {
+        unsigned int *w = l.words + 2 * world + scratch;
+        if (g_drv.WriteValue32((CUstream)st, (CUdeviceptr)w, value, 0) != CUDA_SUCCESS) fail(-36, "cuStreamWriteValue32");
+        check(cudaMemcpyAsync(remote, w, sizeof(unsigned int), cudaMemcpyDefault, st), "staged flag copy");
+    }
+    void transfer(const std::vector<Xfer> &xs, cudaStream_t st)
+    {
+        struct Item { const Xfer *x; size_t off; };
+        std::map<std::pair<int, int>, std::vector<Item>> groups;    // ordered: the same walk on every rank
+        std::map<std::pair<int, int>, size_t> fill;
+        for (const Xfer &x : xs) {
+            if (!x.count) continue;
+            if (x.src_rank == x.dst_rank) {
+                if (local_of(x.src_rank)) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, st), "self transfer");
+                continue;
+            }
+            size_t &off = fill[{x.src_rank, x.dst_rank}];
+            groups[{x.src_rank, x.dst_rank}].push_back({&x, off});
+            off += x.count * sizeof(double);
+        }
+        for (auto &kv : groups) {                  // ---- sends
+            const int s = kv.first.first, d = kv.first.second;
+            Local *l = local_of(s);
+            if (!l) continue;
+            const unsigned int seq = ++l->seq_out[d];
+            if (seq > 2) wait32(st, l->words + world + d, seq - 2);
+            unsigned char *slot = l->peer_stage[d] + ((size_t)s * 2 + (seq & 1u)) * CAP;
+            for (const Item &it : kv.second)
+                check(cudaMemcpyAsync(slot + it.off, it.x->src, it.x->count * sizeof(double), cudaMemcpyDefault, st), "staged send");
+            post32(st, *l, 0, l->peer_words[d] + s, seq);
+        }
+        for (auto &kv : groups) {                  // ---- receives
+            const int s = kv.first.first, d = kv.first.second;
+            Local *l = local_of(d);
+            if (!l) continue;
+            const unsigned int seq = ++l->seq_in[s];
+            wait32(st, l->words + s, seq);
+            const unsigned char *slot = l->stage + ((size_t)s * 2 + (seq & 1u)) * CAP;
+            for (const Item &it : kv.second)
+                check(cudaMemcpyAsync(it.x->dst, slot + it.off, it.x->count * sizeof(double), cudaMemcpyDeviceToDevice, st), "staged receive");
+            post32(st, *l, 1, l->peer_words[s] + world + d, seq);
+        }
+    }
+};
+
+bool staged_requested()
+{
+    const char *e = getenv("MG_DIST_TRANSPORT");
+    return e && strcmp(e, "staged") == 0;
+}
+
 class EmuComm : public Comm {
 public:
-    explicit EmuComm(int g) { world = g; for (int r = 0; r < g; ++r) local.push_back(r); }
+    std::unique_ptr<StagedTransport> staged;      // MG_DIST_TRANSPORT=staged: the protocol of the real transport, in one process
+    explicit EmuComm(int g)
+    {
+        world = g;
+        for (int r = 0; r < g; ++r) local.push_back(r);
+        if (g > 1 && staged_requested()) {
+            staged.reset(new StagedTransport());
+            bool good = true;
+            for (int r = 0; r < g && good; ++r) good = staged->add_local(r, g);
+            if (!good || !staged->link_in_process()) { staged.reset(); fail(-37, "staged transport: set-up failed"); }
+        }
+    }
+    ~EmuComm() override { cudaDeviceSynchronize(); }
     void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) override
     {
+        if (staged && staged->applicable(xs)) { staged->transfer(xs, stream); return; }
         for (const Xfer &x : xs)
             if (x.count) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, stream), "emu transfer");
     }
@@ -93,6 +269,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -104,7 +281,7 @@ struct NcclApi {
         if (!handle) { fail(-30, std::string("cannot load libnccl.so.2: ") + dlerror()); return false; }
 #define MG_SYM(field, name) field = (decltype(field))dlsym(handle, name); if (!field) { fail(-31, "libnccl.so.2 lacks " name); return false; }
         MG_SYM(GetUniqueId, "ncclGetUniqueId") MG_SYM(CommInitRank, "ncclCommInitRank") MG_SYM(CommDestroy, "ncclCommDestroy")
-        MG_SYM(Send, "ncclSend") MG_SYM(Recv, "ncclRecv") MG_SYM(AllReduce, "ncclAllReduce") MG_SYM(GroupStart, "ncclGroupStart")
+        MG_SYM(Send, "ncclSend") MG_SYM(Recv, "ncclRecv") MG_SYM(AllReduce, "ncclAllReduce") MG_SYM(AllGather, "ncclAllGather") MG_SYM(GroupStart, "ncclGroupStart")
         MG_SYM(GroupEnd, "ncclGroupEnd") MG_SYM(GetErrorString, "ncclGetErrorString")
 #undef MG_SYM
         return true;
@@ -122,8 +299,64 @@ public:
         fail(-32, std::string(what) + ": " + g_nccl.GetErrorString(r));
         return false;
     }
+    std::unique_ptr<StagedTransport> staged;      // MG_DIST_TRANSPORT=staged
+
+    // Collective: every rank allocates its staging area, the IPC handles are all-gathered, every rank
+    // maps the others' areas, and the transport is switched on only if ALL ranks succeeded.
+    bool setup_staged()
+    {
+        struct Pack { cudaIpcMemHandle_t stage, words; };
+        cudaStream_t st = ctx().stream;
+        std::unique_ptr<StagedTransport> t(new StagedTransport());
+        int good = (t->add_local(rank, world) && g_drv.load()) ? 1 : 0;
+        Pack mine;
+        memset(&mine, 0, sizeof mine);
+        if (good) {
+            StagedTransport::Local &l = t->locals[0];
+            good = cudaIpcGetMemHandle(&mine.stage, l.stage) == cudaSuccess && cudaIpcGetMemHandle(&mine.words, l.words) == cudaSuccess;
+        }
+        unsigned char *dsend = nullptr, *drecv = nullptr;
+        int *dflag = nullptr;
+        std::vector<Pack> packs((size_t)world);
+        bool coll = cudaMalloc(&dsend, sizeof(Pack)) == cudaSuccess && cudaMalloc(&drecv, (size_t)world * sizeof(Pack)) == cudaSuccess &&
+                    cudaMalloc(&dflag, sizeof(int)) == cudaSuccess;
+        if (!coll) { fail(-37, "staged transport: cudaMalloc"); return false; }
+        cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice);
+        coll = ok(g_nccl.AllGather(dsend, drecv, sizeof(Pack), ncclChar, comm, st), "ncclAllGather (IPC handles)");
+        cudaStreamSynchronize(st);
+        cudaMemcpy(packs.data(), drecv, (size_t)world * sizeof(Pack), cudaMemcpyDeviceToHost);
+        if (good && coll) {
+            StagedTransport::Local &l = t->locals[0];
+            t->ipc_opened.assign((size_t)world, 0);
+            l.peer_stage[rank] = l.stage;
+            l.peer_words[rank] = l.words;
+            for (int q = 0; q < world && good; ++q) {
+                if (q == rank) continue;
+                void *a = nullptr, *b = nullptr;
+                good = cudaIpcOpenMemHandle(&a, packs[q].stage, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+                       cudaIpcOpenMemHandle(&b, packs[q].words, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                if (good) { l.peer_stage[q] = (unsigned char *)a; l.peer_words[q] = (unsigned int *)b; t->ipc_opened[q] = 1; }
+            }
+            if (!good) cudaGetLastError();
+        }
+        int all = (good && coll) ? 1 : 0;
+        cudaMemcpy(dflag, &all, sizeof(int), cudaMemcpyHostToDevice);
+        ok(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, comm, st), "ncclAllReduce (staged transport)");
+        cudaStreamSynchronize(st);
+        cudaMemcpy(&all, dflag, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(dsend); cudaFree(drecv); cudaFree(dflag);
+        if (all) {
+            t->ready = true;
+            staged = std::move(t);
+            if (rank == 0 && getenv("MG_DIST_TRACE")) fprintf(stderr, "[mg trace] staged transport ready on %d ranks (CUDA IPC)\n", world);
+        }
+        else if (rank == 0) fprintf(stderr, "[ WARNING ]: staged transport unavailable on some rank; using NCCL send/recv\n");
+        return all != 0;
+    }
+
     void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) override
     {
+        if (staged && staged->applicable(xs)) { staged->transfer(xs, stream); return; }
         ok(g_nccl.GroupStart(), "ncclGroupStart");
         for (const Xfer &x : xs) {
             if (!x.count) continue;
@@ -900,6 +1133,7 @@ int mgDistInit(int rank, int world, const void *id128)
     memcpy(&id, id128, sizeof id);
     if (!cm->ok(g_nccl.CommInitRank(&cm->comm, world, id, rank), "ncclCommInitRank")) return 2;
     g_nccl_comm = std::move(cm);
+    if (world > 1 && staged_requested()) g_nccl_comm->setup_staged();   // collective; falls back to NCCL transfers if any rank fails
     return 0;
 }
 
@@ -1023,6 +1257,8 @@ void mgDistShutdown(void)
 {
     if (g_nccl_comm) {
         cudaStreamSynchronize(ctx().stream);
+        cudaStreamSynchronize(ctx().comm_stream);
+        g_nccl_comm->staged.reset();
         g_nccl.CommDestroy(g_nccl_comm->comm);
         g_nccl_comm.reset();
     }

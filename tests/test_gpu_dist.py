@@ -92,6 +92,30 @@ def test_overlapped_exchange_matches_single_gpu(mg, overlapped, text, world, thr
     compare(mg, texts[text], world, threshold)
 
 
+@pytest.fixture
+def staged(monkeypatch):
+    """MG_DIST_TRANSPORT=staged: row transfers through staging buffers, copy engines and stream
+    memory operations (the emulated ranks run the protocol of the real IPC transport in one process)."""
+    monkeypatch.setenv("MG_DIST_TRANSPORT", "staged")
+    yield
+    monkeypatch.delenv("MG_DIST_TRANSPORT", raising=False)
+
+
+@pytest.mark.parametrize("text,world,threshold,overlap", [
+    ("v1024", 2, 256, False), ("v1024", 8, 256, False), ("w512", 4, 128, False), ("trigger512", 4, 128, False),
+    ("step5", 3, 128, False), ("restart", 4, 128, False), ("v4096", 4, 1024, False),
+    ("v1024", 4, 256, True), ("w512", 4, 128, True), ("v4096", 8, 1024, True)])
+def test_staged_transport_matches_single_gpu(mg, staged, monkeypatch, text, world, threshold, overlap):
+    """Sequence flags, slot parity, offsets and acknowledgements of the staged transport: same bits
+    as the single-GPU run, in line and with the exchange on its own stream behind the edge launch."""
+    if overlap:
+        monkeypatch.setenv("MG_DIST_OVERLAP", "1")
+    texts = {"v1024": mg.cycles.v_cycle(1024, 8), "w512": mg.cycles.w_cycle(512, 8, levels=4, step=2, tol=1e-7),
+             "trigger512": mg.cycles.v_cycle(512, 8, step=-1), "step5": mg.cycles.v_cycle(512, 16, step=5),
+             "restart": mg.cycles.v_cycle(512, 8, step=2, cycles=2), "v4096": mg.cycles.v_cycle(4096, 8)}
+    compare(mg, texts[text], world, threshold)
+
+
 def test_large_grid_slabs(mg):
     compare(mg, mg.cycles.v_cycle(4096, 8), 8, 1024)
 
