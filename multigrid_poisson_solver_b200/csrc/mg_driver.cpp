@@ -160,7 +160,7 @@ public:
                 if (con_step == 0) { if (c >= tok.size()) return 0; st = (int)tok[c++]; } else st = con_step;
                 if (con_N == 0) { if (c >= tok.size()) return 0; nn = (int)tok[c++]; }
                 else { if (p + 1 >= ladder.size()) return 0; nn = ladder[++p]; }
-                if (st == 0) return 0;                    // FMG placeholder: leave it to the node-by-node path
+                if (st == 0 || st < -1) return 0;         // FMG placeholder / zero-sweep quirk: leave it to the node-by-node path
                 const bool restart = sim_init == 0 && base_depth + sizes.size() - 1 == 1;
                 kind.push_back(-1); step.push_back(st); zero.push_back(restart ? 0 : 1); Nop.push_back(sizes.back());
                 nextN.push_back(nn); option.push_back(0); target.push_back(0.0);
@@ -174,6 +174,7 @@ public:
             } else if (node == 1) {
                 int st;
                 if (con_step == 0) { if (c >= tok.size()) return 0; st = (int)tok[c++]; } else st = con_step;
+                if (st < -1) return 0;
                 if (con_N != 0 && p > 0) --p;
                 sizes.pop_back();
                 if (base_depth + sizes.size() - 1 == 1) sim_init = 0;
@@ -377,7 +378,11 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
                 int done = 0;
                 if (step == -1) done = cy.trigger_smooth(*l, L);
                 else if (step > 0) { l->step = done = step; }
-                const int r = cy.record(1, l->N, done, step == -1 ? l->smoothing_error : 0.0);
+                else if (step < -1) {                                 // :410-421: doSmoothing with a negative count = 0 sweeps + error
+                    doSmoothing(l->N, L, l->U, l->F, step, &l->smoothing_error);
+                    l->step = done = step;
+                }
+                const int r = cy.record(1, l->N, done, step < 0 ? l->smoothing_error : 0.0);
                 if (slot >= 0) {
                     cy.defer(r, slot, false);
                     if (sync_each_node) { cy.harvest(); l->smoothing_error = *mgScalarSlot(slot); }
@@ -395,7 +400,7 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
             mgGridFree(tmp);                                          // :371
             int done = 0;
             if (step == -1) done = cy.trigger_smooth(*l, L);
-            else if (step > 0) { doSmoothing(l->N, L, l->U, l->F, step, &l->smoothing_error); l->step = done = step; }
+            else if (step != 0) { doSmoothing(l->N, L, l->U, l->F, step, &l->smoothing_error); l->step = done = step; }
             if (!quiet && step != 0) cy.log_smoothing(*l, done);
             cy.record(1, l->N, done, l->smoothing_error);
         } else {

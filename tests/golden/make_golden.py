@@ -37,7 +37,20 @@ CYCLES = {
     "W_full_64": cy.w_cycle(64, 8, step=1, tol=1e-7),
     "V_lu_coarse": cy.v_cycle(32, 8, step=2, tol=0.0, option=0),
     "V_offset_domain": cy.v_cycle(64, 8, step=3, tol=1e-7, L=2.0, min_x=-0.5, min_y=0.25),
+    # the remaining (con_step, con_N) parser modes and the step == 0 / negative-step nodes
+    # (MG_solver_CPU.cpp:171-189, :241-243, :296-299, :331-344, :410-421)
+    # (0, 1): per-node steps on the automatic ladder; the step-0 "-1" node only advances the ladder
+    # position (:174-179), so the next restriction goes 32 -> 8; the last "1" node skips its smoothing
+    "mode_nodestep_autoN": cy.manual([(-1, 2, 0), (-1, 0, 0), (-1, 3, 0), (0, 1e-7, 1), (1, 2), (1, 0)], 64, 8, con_step=0, con_N=1),
+    # (3, 0): fixed steps, per-node next_N (non-nested sizes)
+    "mode_fixedstep_manualN": cy.manual([(-1, 0, 21), (-1, 0, 11), (0, 1e-8, 1), (1, 0), (1, 0)], 45, 11, con_step=3, con_N=0),
+    # (0, 2): per-node steps on the N -> N-1 ladder, with a step of -2 (zero sweeps, error still evaluated)
+    "mode_nodestep_minus1": cy.manual([(-1, 1, 0), (-1, -2, 0), (-1, 2, 0), (0, 1e-6, 1), (1, 1), (1, -2), (1, 3)], 24, 21, con_step=0, con_N=2),
+    # (0, 0) with step 0 on both node kinds: the step-0 "-1" node reads its next_N and does nothing
+    "mode_manual_step0": cy.manual([(-1, 2, 16), (-1, 0, 12), (-1, 1, 8), (0, 1e-7, 1), (1, 0), (1, 2)], 32, 8),
 }
+BINARY_LOGS = ("test", "Vcycle", "VcycleTrigger", "Wcycle", "mode_nodestep_autoN", "mode_fixedstep_manualN", "mode_nodestep_minus1",
+               "mode_manual_step0")
 
 
 def main():
@@ -58,14 +71,14 @@ def main():
         json.dump(out, f, indent=1)
 
     # real binary logs (run from tests/golden so that argv[2] is a bare file name)
-    for name in ("test", "Vcycle", "VcycleTrigger", "Wcycle"):
+    for name in BINARY_LOGS:
         p = subprocess.run([po.REF_BIN, "1", "cycle_%s.txt" % name], cwd=HERE, capture_output=True, text=True, check=True)
         log = "\n".join(l for l in p.stdout.splitlines() if not l.startswith("Time Used"))
         with open(os.path.join(HERE, "MG_CPU_%s.log" % name), "w") as f:
             f.write(log + "\n")
         csv = os.path.join(HERE, "Sol_CPU_cycle_%s.txt" % name)
-        if name == "test":
-            os.replace(csv, os.path.join(HERE, "MG_CPU_test.csv"))
+        if name == "test" or name.startswith("mode_"):
+            os.replace(csv, os.path.join(HERE, "MG_CPU_%s.csv" % name))
         else:
             os.remove(csv)
 

@@ -43,8 +43,11 @@ def same(a, b):
     return np.asarray(a).tobytes() == np.asarray(b).tobytes()
 
 
+MODE_CYCLES = ["mode_nodestep_autoN", "mode_fixedstep_manualN", "mode_nodestep_minus1", "mode_manual_step0"]
+
+
 @pytest.mark.parametrize("name", ["test", "Vcycle", "VcycleTrigger", "Wcycle", "V_minus_one_ladder", "V_restart_x2",
-                                  "manual_nonnested", "W_full_64", "V_lu_coarse", "V_offset_domain"])
+                                  "manual_nonnested", "W_full_64", "V_lu_coarse", "V_offset_domain"] + MODE_CYCLES)
 def test_cycle_matches_reference_golden(name, goldens, golden_dir):
     g = goldens[name]
     r = po.run_cycle(os.path.join(golden_dir, "cycle_%s.txt" % name))
@@ -170,11 +173,28 @@ def test_oracle_equals_reference_exact_solver(N, tol, opt, orc):
 def test_driver_matches_real_binary_log(golden_dir, tmp_path):
     """The oracle's driver must print-equal the real ./MG_CPU at %lf precision."""
     import subprocess
-    for name in ("Vcycle", "VcycleTrigger", "Wcycle"):
+    for name in ["Vcycle", "VcycleTrigger", "Wcycle"] + MODE_CYCLES:
         log = open(os.path.join(golden_dir, "MG_CPU_%s.log" % name)).read().splitlines()
         errs = [l.split("=")[1].strip() for l in log if l.strip().startswith("Error =")]
         steps = [int(l.split("=")[1]) for l in log if "Smoothing Steps" in l]
+        sizes = [int(l.split("=")[1]) for l in log if "Current Grid Size" in l]
         r = po.run_cycle(os.path.join(golden_dir, "cycle_%s.txt" % name))
-        mine = ["%f" % t["err"] for t in r["trace"] if t["node"] != 0] + ["%f" % r["mg_error"]]
-        assert mine == errs
-        assert [t["steps"] for t in r["trace"] if t["node"] != 0] == steps
+        # a "1" node with step 0 prints no smoothing block (:410-412); a step-0 "-1" node does nothing at all
+        smooth = [t for t in r["trace"] if t["node"] != 0 and not (t["node"] == 1 and t["steps"] == 0)]
+        assert ["%f" % t["err"] for t in smooth] + ["%f" % r["mg_error"]] == errs
+        assert [t["steps"] for t in smooth] == steps
+        assert [t["N"] for t in r["trace"] if not (t["node"] == 1 and t["steps"] == 0)] == sizes
+
+
+def csv_text(U, N):
+    """doPrint2File's layout (MG_solver_CPU.cpp:735-754): %lf, row j = N-1 first."""
+    g = np.asarray(U).reshape(N, N)
+    return "".join(",".join("%f" % v for v in g[j]) + "\n" for j in range(N - 1, -1, -1))
+
+
+@pytest.mark.parametrize("name", ["test"] + MODE_CYCLES)
+def test_final_grid_matches_real_binary_csv(name, golden_dir):
+    """Control flow of the remaining parser modes (step 0 / negative steps, (0,!=0), (!=0,0)) is pinned by
+    the solution file the real ./MG_CPU wrote for the same cycle file (6 decimals: any wrong branch shows)."""
+    r = po.run_cycle(os.path.join(golden_dir, "cycle_%s.txt" % name))
+    assert csv_text(r["U"], r["N"]) == open(os.path.join(golden_dir, "MG_CPU_%s.csv" % name)).read()
