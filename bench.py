@@ -149,48 +149,148 @@ class ClockSampler:
         return out
 
 
-# ----------------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference_run(sample_N, threads, repeats, nmax):
-    """Times V-cycles of the same shape at sample_N with the reference's own operators
-    (oracle/_ref/libmgref.so, built -O0 -fopenmp exactly as src/Makefile:8) when present, else
-    the oracle port.  Returns (kind, [seconds per cycle], mg_error)."""
-    from oracle import pyoracle as po
+# ----------------------------------------------------------------------------- workloads
+def workloads():
+    """BASELINE.json configs as bench workloads.  `N` = N_max, `sample_N` = N_max of the CPU reference run
+    (equal to N when the reference can run the real thing in bounded time and memory)."""
     from multigrid_poisson_solver_b200 import cycles
-    path = write_cycle(cycles.v_cycle(sample_N, 8))
-    if po.have_ref():
-        kind, ops = "reference", po.ref_ops(threads)
-    else:
-        kind, ops = "port", None
-    times, err = [], None
-    for _ in range(repeats):
-        r = po.run_cycle(path, ops=ops, threads=threads, want_U=False)
-        times.append(r["time_ms"] / 1000.0)      # the reference's own timer span (:156,:429)
+    return {
+        # configs[1]'s shape at the size the metric is quoted on: the headline
+        "v16384": dict(N=16384, text=lambda n: cycles.v_cycle(n, 8), sample_N=16384, metric=METRIC,
+                       what="Vcycle.txt shape (con_step=3, con_N=1, GS 1e-7 opt 1) at N_max=%d N_min=8"),
+        "v8192": dict(N=8192, text=lambda n: cycles.v_cycle(n, 8), sample_N=8192, metric="V-cycles/sec at N=8192 fp64",
+                      what="BASELINE config 2: Vcycle.txt shape (con_step=3, con_N=1) at N_max=%d N_min=8"),
+        "w16384": dict(N=16384, text=lambda n: cycles.w_cycle(n, 16, tol=1e-8), sample_N=4096, metric="W-cycles/sec at N=16384 fp64",
+                       what="BASELINE config 3: Wcycle.txt recursion over the whole ladder N_max=%d ... 16 (GS 1e-8 at N=16)"),
+        "trigger32768": dict(N=32768, text=lambda n: cycles.v_cycle(n, 8, step=-1), sample_N=8192,
+                             metric="error-trigger V-cycles/sec at N=32768 fp64",
+                             what="BASELINE config 4: VcycleTrigger.txt shape (con_step=-1) at N_max=%d N_min=8"),
+        "trigger16384": dict(N=16384, text=lambda n: cycles.v_cycle(n, 8, step=-1), sample_N=8192,
+                             metric="error-trigger V-cycles/sec at N=16384 fp64",
+                             what="VcycleTrigger.txt shape (con_step=-1) at N_max=%d N_min=8"),
+    }
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def stock_main_run(text, threads, timeout_s=1200):
+    """Runs the UNMODIFIED reference program (oracle/_ref/MG_CPU = g++ -fopenmp, no -O, of
+    /root/reference/src/MG_solver_CPU.cpp + linkedlist.cpp, exactly src/Makefile:8) on a cycle file and
+    reads ITS OWN report: `Time Used` = omp_get_wtime() span of the node loop (MG_solver_CPU.cpp:156,
+    :429-451) and the final `Error`.  The program then dumps the solution as CSV (2.4 GB of fprintf at
+    N = 16384, :454-457); that dump is not part of the metric, so the process is stopped once the report
+    line has been read (stdout is made line-buffered with stdbuf, or a pty when stdbuf is missing) and
+    the output name is pre-linked to /dev/null in a scratch directory that is deleted afterwards."""
+    import shutil
+    from oracle import pyoracle as po
+    if not os.path.exists(po.REF_BIN):
+        return None
+    d = tempfile.mkdtemp(prefix="mgref_")
+    try:
+        with open(os.path.join(d, "c.txt"), "w") as f:
+            f.write(text)
+        os.symlink("/dev/null", os.path.join(d, "Sol_CPU_c.txt"))
+        cmd = [po.REF_BIN, str(threads), "c.txt"]
+        master = None
+        if shutil.which("stdbuf"):
+            proc = subprocess.Popen(["stdbuf", "-oL"] + cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            stream = proc.stdout
+        else:
+            import pty
+            master, slave = pty.openpty()
+            proc = subprocess.Popen(cmd, cwd=d, stdout=slave, stderr=subprocess.DEVNULL)
+            os.close(slave)
+            stream = os.fdopen(master, "r", errors="replace")
+        out = {"errors": [], "time_ms": None, "mg_error": None}
+        t0 = time.time()
+        final = False
+        try:
+            for line in stream:
+                line = line.strip()
+                if line.startswith("===== Final Result"):
+                    final = True
+                elif line.startswith("Error ="):
+                    v = float(line.split("=")[1])
+                    if final:
+                        out["mg_error"] = v
+                    else:
+                        out["errors"].append(v)
+                elif line.startswith("Time Used ="):
+                    out["time_ms"] = float(line.split("=")[1].split()[0])
+                    break
+                if time.time() - t0 > timeout_s:
+                    break
+        except OSError:
+            pass
+        proc.kill()                      # our own child, by PID: skips the CSV dump
+        proc.wait()
+        out["wall_s"] = time.time() - t0
+        return out if out["time_ms"] is not None else None
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def cpu_reference(wl, threads, runs):
+    """`runs` timed cycles of workload `wl` on the host cores.  Returns dict(kind, ms=[...] per cycle AT wl['N'],
+    sample=text, mg_error).  kind "reference": the stock main(); when the workload is too big for a bounded CPU run the
+    same cycle shape is run at sample_N and scaled by the DOF ratio (a cycle's work is linear in N^2), which the sample text says.
+    kind "port" (oracle restatement, -O2) only if oracle/_ref is missing."""
+    from oracle import pyoracle as po
+    N, sN = wl["N"], wl["sample_N"]
+    scale = (N / sN) ** 2
+    ms, err, kind = [], None, "reference"
+    for _ in range(runs):
+        r = stock_main_run(wl["text"](sN), threads)
+        if r is None:
+            kind = "port"
+            path = write_cycle(wl["text"](sN))
+            q = po.run_cycle(path, threads=threads, want_U=False)
+            os.unlink(path)
+            r = {"time_ms": q["time_ms"], "mg_error": q["mg_error"]}
+        ms.append(r["time_ms"] * scale)
         err = r["mg_error"]
-    os.unlink(path)
-    return kind, times, err
+    what = ("stock MG_CPU main() (reference sources compiled -O0 -fopenmp as src/Makefile:8), %d OpenMP threads, its own `Time Used` "
+            "(omp_get_wtime span of the node loop, MG_solver_CPU.cpp:156,:429-451); CSV dump skipped" % threads) if kind == "reference" else \
+           ("oracle restatement of main() (-O2), %d threads, the reference's timer span" % threads)
+    if sN == N:
+        sample = "%s; the whole workload: %s, %d cycle(s) run" % (what, wl["what"] % N, runs)
+    else:
+        sample = "%s; bounded sample: the same cycle shape at N_max=%d (%d cycle(s)), scaled to N_max=%d by the DOF ratio %.0f" % (
+            what, sN, runs, N, scale)
+    return dict(kind=kind, ms=ms, sample=sample, mg_error=err, same_config=(sN == N))
 
 
 def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on the arm's workload.  The stock main()
+    at N = 16384 needs ~15-45 s per cycle, so the run is capped at 1 warm-up + 2 timed cycles whatever
+    --steps/--warmup ask for (the line says so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    sample_N = args.ref_sample
-    kind, times, err = cpu_reference_run(sample_N, threads, args.warmup + args.steps, args.nmax)
-    timed = times[args.warmup:]
-    sec = sum(timed) / len(timed)
-    scale = (sample_N / args.nmax) ** 2           # DOF ratio: a V-cycle's work is linear in N^2
-    value = scale / sec
-    sample = ("V-cycle N_max=%d (same shape: 3+3 sweeps, N/2 ladder to 8, GS 1e-7) timed with the reference's own "
-              "timer span; V-cycles/s at N=%d obtained by the DOF ratio (%d/%d)^2" % (sample_N, args.nmax, sample_N, args.nmax))
+    wl = workloads()[args.config]
+    if args.nmax:
+        wl["N"] = args.nmax
+        wl["sample_N"] = min(wl["sample_N"], args.nmax)
+    warm, timed = min(args.warmup, 1), max(1, min(args.steps, 2))
+    world = max(1, args.gpus)
+    r = cpu_reference(wl, threads, warm + timed)
+    ms = r["ms"][warm:]
+    ms_per_cycle = sum(ms) / len(ms)
+    value = 1000.0 / ms_per_cycle
+    cfg = {"workload": wl["what"] % wl["N"], "steps_run": timed, "warmup_run": warm,
+           "steps_note": "capped at 1 warm-up + 2 timed cycles of the stock main() (each 15-45 s at N=16384); requested --steps %d --warmup %d"
+                         % (args.steps, args.warmup)}
+    if world > 1:
+        cfg["multi_gpu_note"] = ("the %d-GPU arm's value is in units of the 1-GPU workload (16384^2 fine points per GPU, weak scaling); a "
+                                 "V-cycle's work is linear in the DOF count, so the reference's value in the same unit is its N=16384 rate" % world)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * sec / scale, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Vcycle.txt shape at N_max=%d N_min=8 step=3 (CPU sample at N_max=%d)" % (args.nmax, sample_N)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+        "warmup": warm, "ms_per_step": ms_per_cycle, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "fine_dof_cycles_per_s": value * args.nmax ** 2, "sample_ms_per_cycle": 1000.0 * sec, "sample_mg_error": err,
+        "fine_dof_cycles_per_s": value * wl["N"] ** 2, "mg_error": r["mg_error"], "ms_per_cycle_runs": r["ms"],
+        "same_config": r["same_config"],
     }
     print(json.dumps(line))
     return 0
@@ -203,8 +303,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nmax", type=int, default=16384)
-    ap.add_argument("--ref-sample", type=int, default=4096, help="N_max of the bounded CPU sample")
+    ap.add_argument("--config", default="v16384", choices=["v16384", "v8192", "w16384", "trigger32768", "trigger16384"],
+                    help="workload (BASELINE.json configs); the default is the one the metric is quoted on")
+    ap.add_argument("--nmax", type=int, default=0, help="override N_max of the workload")
     ap.add_argument("--unfused", action="store_true", help="one ABI operator per reference call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -249,20 +350,25 @@ def main():
         return multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, local, barrier, max_over_ranks,
                              hbm_peak, peak_src)
 
-    N = args.nmax
+    wl = workloads()[args.config]
+    if args.nmax:
+        wl["N"] = args.nmax
+        wl["sample_N"] = min(wl["sample_N"], args.nmax)
+    N = wl["N"]
     n = N * N
-    path = write_cycle(cycles.v_cycle(N, 8))
+    path = write_cycle(wl["text"](N))
+    max_recs = 8192
     base_flags = (mg.RUN_UNFUSED if args.unfused else mg.RUN_FUSED) | mg.RUN_QUIET | mg.RUN_NO_FINAL_ERROR
     flags = base_flags | mg.RUN_SKIP_SOURCE
 
     # ---- device-resident run -------------------------------------------------------------
     F = mg.DeviceGrid(N)
     lib.getSource(N, 1.0, F.ptr, 0.0, 0.0)
-    recs = (api.TraceRec * 64)()
+    recs = (api.TraceRec * max_recs)()
     res = api.CycleResult()
 
     def one_cycle():
-        rc = lib.mgRunCycleFile(os.fsencode(path), flags, F.ptr, None, recs, 64, res)
+        rc = lib.mgRunCycleFile(os.fsencode(path), flags, F.ptr, None, recs, max_recs, res)
         if rc != 0:
             raise SystemExit("mgRunCycleFile failed: %d %s" % (rc, lib.mgLastError().decode()))
         return res.launches, res.time_ms
@@ -318,7 +424,7 @@ def main():
 
         def single(k):
             for i in range(k):
-                rc = lib.mgRunCycleFileHost(os.fsencode(path), base_flags, hF[i % 2].data_ptr(), hU[i % 2].data_ptr(), recs, 64, res)
+                rc = lib.mgRunCycleFileHost(os.fsencode(path), base_flags, hF[i % 2].data_ptr(), hU[i % 2].data_ptr(), recs, max_recs, res)
                 if rc != 0:
                     raise SystemExit("mgRunCycleFileHost failed: %d" % rc)
 
@@ -345,16 +451,16 @@ def main():
     roof = dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, args.unfused)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Vcycle.txt shape (con_step=3, con_N=1, GS 1e-7 opt 1) at N_max=%d N_min=8, 1 grid per GPU" % N,
+        "config": {"workload": (wl["what"] % N) + ", 1 grid per GPU", "name": args.config,
                    "driver": "unfused (8 ABI operators)" if args.unfused else "fused (mgDownLeg/mgUpLeg)",
                    "l2": "inputs exceed L2 (%.1f GiB per grid vs 126 MB)" % (8 * n / 2 ** 30),
                    "parallelism": "1 GPU" if world == 1 else "%d independent replicas (slab partition: see DESIGN.md)" % world},
         "fine_dof_cycles_per_s": value * n,
         "device_ms_per_cycle_node_loop": inner_ms / args.steps,
-        "mg_error": mg_error, "trace_errors": [t["err"] for t in trace if t["node"] != 0],
+        "mg_error": mg_error, "trace_errors": [t["err"] for t in trace if t["node"] != 0][:48],
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof,
         "cycle_roofline": {"unfused_algorithmic_bytes": 357.0 * n, "achieved_GBs": 357.0 * n / (ms_per_step * 1e6),
                            "note": "BASELINE.md 3: 357*N^2 B per unfused V-cycle; effective bandwidth may exceed HBM peak when legs are fused"},
@@ -362,14 +468,9 @@ def main():
 
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        kind, times, err = cpu_reference_run(args.ref_sample, threads, 2, N)
-        sec = min(times)
-        scale = (args.ref_sample / N) ** 2
-        line["cpu_baseline"] = {
-            "value": scale / sec, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": "V-cycle N_max=%d, same shape, reference operators (-O0 -fopenmp as src/Makefile:8) on %d threads, "
-                      "best of 2, %.0f ms/cycle; scaled to N=%d by the DOF ratio" % (args.ref_sample, threads, 1000 * sec, N),
-            "sample_mg_error": err}
+        r = cpu_reference(wl, threads, 1)
+        line["cpu_baseline"] = {"value": 1000.0 / r["ms"][0], "unit": UNIT, "cores": threads, "kind": r["kind"], "sample": r["sample"],
+                                "ms_per_cycle": r["ms"][0], "mg_error": r["mg_error"], "same_config": r["same_config"]}
     os.unlink(path)
     if rank == 0:
         print(json.dumps(line))
@@ -385,7 +486,7 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
     """Weak scaling of the row-slab driver: the grid grows with the GPU count so that every GPU keeps
     16384^2 fine points; one process per GPU, NCCL halo exchange, levels < 2048 rows on rank 0."""
     threshold = int(os.environ.get("MG_DIST_THRESHOLD", "2048"))
-    N = WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256) if args.nmax == 16384 else args.nmax
+    N = args.nmax if args.nmax else WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256)
     n = N * N
     base_n = 16384 * 16384
 
