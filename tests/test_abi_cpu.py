@@ -150,8 +150,8 @@ def test_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--ref-sample", "128",
-                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--nmax", "128",
+                          "--steps", "5", "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -162,6 +162,10 @@ def test_reference_arm_prints_the_contract_line():
         assert key in d, key
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # the stock main() is capped at 1 warm-up + 2 timed cycles whatever was asked for, and the line says what ran
+    assert d["steps"] == 2 and d["warmup"] == 1 and "requested --steps 5 --warmup 3" in d["config"]["steps_note"]
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert "stock MG_CPU main()" in d["cpu_baseline"]["sample"] and d["same_config"] is True
 
 
 def test_segment_plan_properties_random():
