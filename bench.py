@@ -484,8 +484,8 @@ WEAK_N = {1: 16384, 2: 23168, 4: 32768, 8: 46336}   # N^2 per GPU constant (1638
 
 def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, local, barrier, max_over_ranks, hbm_peak, peak_src):
     """Weak scaling of the row-slab driver: the grid grows with the GPU count so that every GPU keeps
-    16384^2 fine points; one process per GPU, NCCL halo exchange, levels < 2048 rows on rank 0."""
-    threshold = int(os.environ.get("MG_DIST_THRESHOLD", "2048"))
+    16384^2 fine points; one process per GPU, halo rows by peer stores of the fused kernels, levels < 1024 rows redundant on every rank."""
+    threshold = int(os.environ.get("MG_DIST_THRESHOLD", "1024"))
     N = args.nmax if args.nmax else WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256)
     n = N * N
     base_n = 16384 * 16384
@@ -531,34 +531,44 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
     chk = mg.run_cycle_dist(path, threshold, mg.RUN_FUSED | mg.RUN_QUIET | mg.RUN_SKIP_SOURCE)
     mg_error = chk["mg_error"]
 
-    # ---- end to end: every rank uploads its source slab from pinned memory and reads its rows back
+    # ---- end to end: mgDistRunCycleFileHostBatch, one problem per step -- every rank uploads its source slab from pinned
+    # memory, the ranks run the V-cycle together, every rank reads its rows of the solution back into pinned memory;
+    # consecutive steps are double-buffered per rank (upload i+1 / cycle i / download i-1 on two copy streams).
     e2e = None
     if not args.no_e2e:
         r0, rows, olo, ohi = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
         lib.mgDistSourceSlab(N, threshold, C.byref(r0), C.byref(rows), C.byref(olo), C.byref(ohi))
-        hF = torch.empty(max(rows.value, 1) * N, dtype=torch.float64).pin_memory()
-        hU = torch.empty(max(ohi.value - olo.value, 1) * N, dtype=torch.float64).pin_memory()
-        lib.mgDistDownloadSource(N, hF.data_ptr())
-        e2e_steps = max(2, min(args.steps, 5))
+        hF = [torch.empty(max(rows.value, 1) * N, dtype=torch.float64).pin_memory() for _ in range(2)]
+        hU = [torch.empty(max(ohi.value - olo.value, 1) * N, dtype=torch.float64).pin_memory() for _ in range(2)]
+        for h in hF:
+            lib.mgDistDownloadSource(N, h.data_ptr())
+        e2e_steps = max(2, min(args.steps, 10))
+        e2e_flags = mg.RUN_FUSED | mg.RUN_QUIET | mg.RUN_NO_FINAL_ERROR
 
-        def one_e2e():
-            lib.mgDistUploadSource(N, threshold, hF.data_ptr())
-            one_cycle(hU.data_ptr())
+        def batch(k):
+            Fp, Up, rs = (C.c_void_p * k)(), (C.c_void_p * k)(), (api.CycleResult * k)()
+            for i in range(k):
+                Fp[i], Up[i] = hF[i % 2].data_ptr(), hU[i % 2].data_ptr()
+            rc = lib.mgDistRunCycleFileHostBatch(os.fsencode(path), threshold, e2e_flags, k, Fp, Up, rs)
+            if rc != 0:
+                raise SystemExit("mgDistRunCycleFileHostBatch failed: %d %s" % (rc, lib.mgLastError().decode()))
 
-        one_e2e()
+        batch(2)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            one_e2e()
+        batch(e2e_steps)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1000.0 * wall)) / e2e_steps
         e2e = {"value": (n / base_n) * 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * rows.value * N,
                "d2h_bytes_per_step": 8 * (ohi.value - olo.value) * N, "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "call": "per rank: mgDistUploadSource(pinned slab) + mgDistRunCycleFile(U rows -> pinned host); bytes are per rank"}
+               "call": "mgDistRunCycleFileHostBatch on every rank (one problem per step: pinned source slab -> device, V-cycle on the "
+                       "slabs, owned rows of U -> pinned host; upload of step i+1 and download of step i-1 overlap the cycle of step i); "
+                       "bytes are per rank"}
+        del hF, hU
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -567,8 +577,9 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
         "config": {"workload": "Vcycle.txt shape (con_step=3, con_N=1, GS 1e-7 opt 1) at N_max=%d N_min=8: one grid row-slab "
                                "partitioned over %d GPUs, 16384^2 fine points per GPU" % (N, world),
                    "value_is": "V-cycles/s x (N_max/16384)^2, i.e. in units of the 1-GPU workload",
-                   "driver": "mgDistRunCycleFile: fused nodes on row slabs, NCCL send/recv halo exchange (%d rows), "
-                             "levels < %d rows agglomerated on rank 0" % (8, threshold),
+                   "driver": "mgDistRunCycleFile: fused nodes on row slabs; the %d halo rows go into the neighbours' slabs by peer stores "
+                             "of the fused kernel itself (CUDA IPC over NVLink, flag words + stream waits, no communication kernel); levels "
+                             "< %d rows: source broadcast to every rank, coarse sub-cycle redundant on every rank" % (8, threshold),
                    "l2": "inputs exceed L2", "parallelism": "row slabs x%d" % world},
         "fine_dof_cycles_per_s": n * 1000.0 / ms_per_step, "global_ms_per_cycle": ms_per_step, "mg_error": mg_error,
         "trace_errors": [t["err"] for t in trace if t["node"] != 0], "gpu_launches": launches, "clocks": clocks, "e2e": e2e,

@@ -182,10 +182,13 @@ int mgRunCycleFileHostBatch(const char *path, int flags, int n, const double *co
                             mgCycleResult *res);
 
 /* ------------------------------------------------------------ multi-GPU (row slabs)
- * One process per GPU.  Levels with at least `threshold` rows are partitioned into row slabs
- * (one per rank) with halo exchange per fused pass; smaller levels are agglomerated on rank 0.
- * Rendezvous: rank 0 calls mgDistUniqueId, the host program broadcasts the 128 bytes (e.g. with
- * torch.distributed), every rank calls mgDistInit.  NCCL is bound with dlopen at run time. */
+ * One process per GPU.  Levels with at least `threshold` rows are partitioned into row slabs (one per
+ * rank).  The halo rows of every array are stored straight into the neighbours' slabs by the kernel that
+ * produces them (peer memory, CUDA IPC over NVLink) and announced through flag words the neighbours'
+ * streams wait on; smaller levels are agglomerated: their source is broadcast to every rank and the coarse
+ * sub-cycle runs redundantly everywhere.  Rendezvous: rank 0 calls mgDistUniqueId, the host program
+ * broadcasts the 128 bytes (e.g. with torch.distributed), every rank calls mgDistInit (collective).
+ * NCCL (bound with dlopen at run time) carries the rendezvous, the IPC handles and the scalar all-reduces. */
 /* Host-only planning of the slab geometry for a ladder of level sizes: per level
  * [N, distributed?, bound[0..world]] (world+3 ints).  Needs no GPU.  Returns the number of
  * levels, or < 0 if a distributed level cannot be served (odd size / non-fusable pair). */
@@ -195,7 +198,8 @@ int mgDistInit(int rank, int world, const void *id128);
 void mgDistShutdown(void);
 /* Runs a cycle file on all ranks collectively (fused driver, MG_RUN_QUIET / MG_RUN_NO_FINAL_ERROR
  * honoured).  U_own_host, if non-NULL, receives this rank's owned rows [*own_lo, *own_hi) of the
- * final solution (host buffer of at least N_max*N_max doubles is always enough). */
+ * final solution (host buffer of at least N_max*N_max doubles is always enough).  Every rank gets the
+ * complete trace records. */
 int mgDistRunCycleFile(const char *path, int threshold, int flags, double *U_own_host, int *own_lo, int *own_hi,
                        mgTraceRec *recs, int max_recs, mgCycleResult *res);
 /* Host-buffer path of the slab driver: geometry of this rank's top-level slab (rows
@@ -205,16 +209,23 @@ int mgDistRunCycleFile(const char *path, int threshold, int flags, double *U_own
 int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, int *own_hi);
 int mgDistUploadSource(int N, int threshold, const double *F_slab_host);
 int mgDistDownloadSource(int N, double *F_slab_host);
+/* n independent problems through the same cycle file, HOST buffers per rank (pinned for full speed):
+ * F_slab_hosts[i] = this rank's source rows [row0, row0+rows) of problem i, U_own_hosts[i] receives its owned
+ * rows.  Double-buffered like mgRunCycleFileHostBatch (upload i+1 / cycle i / download i-1 on two copy
+ * streams per rank).  Collective; bit-identical to n (mgDistUploadSource, mgDistRunCycleFile) pairs. */
+int mgDistRunCycleFileHostBatch(const char *path, int threshold, int flags, int n, const double *const *F_slab_hosts,
+                                double *const *U_own_hosts, mgCycleResult *res);
 /* doSmoothing on row slabs, repeated (smoothing-only stress of BASELINE config 5): `reps` x `step`
- * Jacobi sweeps from U = 0 on the analytic source, passes of <= 3 fused sweeps with one halo
- * exchange each, error all-reduced per repetition.  N even, up to 65536.  Collective over the ranks
- * of mgDistInit; on one GPU it works without it.  U_own_host (optional): the owned rows. */
+ * Jacobi sweeps from U = 0 on the analytic source, passes of <= 3 fused sweeps whose halo rows go
+ * straight into the neighbours' slabs, error all-reduced per repetition.  N even, up to 65536.  Collective
+ * over the ranks of mgDistInit; on one GPU it works without it.  U_own_host (optional): the owned rows. */
 int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, double *error_out, double *U_own_host,
                        int *own_lo, int *own_hi);
-/* The same slab algorithm with all `world` ranks emulated inside this process on the current GPU
- * (device-to-device copies instead of NCCL): lets the slab logic be verified on one GPU.
- * U_host (N_max^2) receives the assembled solution. */
-int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags, double *U_host,
+/* The same slab algorithm with all `world` ranks emulated inside this process on the current GPU (the same
+ * arenas, peer stores, flag words and stream waits; every rank's passes queued in rank order on one stream):
+ * lets the slab logic be verified on one GPU.  F_host (N_max^2, may be NULL -> getSource on the device) is the
+ * source grid, U_host (N_max^2) receives the assembled solution. */
+int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags, const double *F_host, double *U_host,
                           mgTraceRec *recs, int max_recs, mgCycleResult *res);
 
 /* CSV dump in the reference's format (doPrint2File, MG_solver_CPU.cpp:735-754) from a host array */

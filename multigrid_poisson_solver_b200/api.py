@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(HERE, "libmgb200.so")
+_LIB_PATH = os.path.join(HERE, os.environ.get("MG_LIB_NAME", "libmgb200.so"))   # MG_LIB_NAME: a tuning variant built next to the product library
 
 RUN_UNFUSED, RUN_FUSED, RUN_QUIET, RUN_SKIP_SOURCE, RUN_NO_FINAL_ERROR = 0, 1, 2, 4, 8
 SCALAR_SLOTS = 4096
@@ -83,8 +83,10 @@ ABI = {
     "mgDistDownloadSource": (C.c_int, [C.c_int, _vp]),
     "mgDistRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
-    "mgDistEmuRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(TraceRec), C.c_int,
+    "mgDistEmuRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int,
                                         C.POINTER(CycleResult)]),
+    "mgDistRunCycleFileHostBatch": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
+                                              C.POINTER(CycleResult)]),
 }
 
 _lib = None
@@ -341,14 +343,20 @@ def run_cycle(path, flags=RUN_FUSED | RUN_QUIET, max_recs=8192):
     return _run("mgRunCycleFile", path, flags, None, 0, max_recs)
 
 
-def run_cycle_dist_emulated(path, world, threshold, flags=RUN_FUSED | RUN_QUIET, max_recs=8192):
-    """mgDistEmuRunCycleFile: the row-slab multi-GPU algorithm with all ranks emulated on this GPU."""
+def run_cycle_dist_emulated(path, world, threshold, flags=RUN_FUSED | RUN_QUIET, max_recs=8192, F_host=None):
+    """mgDistEmuRunCycleFile: the row-slab multi-GPU algorithm with all ranks emulated on this GPU.
+    F_host: the source grid (default: getSource on the device)."""
     l = _need()
     N = _n_max(path)
     recs = (TraceRec * max_recs)()
     res = CycleResult()
     U = np.empty(N * N)
-    rc = l.mgDistEmuRunCycleFile(os.fsencode(path), world, threshold, flags, U.ctypes.data, recs, max_recs, C.byref(res))
+    Fp = None
+    if F_host is not None:
+        F_host = np.ascontiguousarray(F_host, dtype=np.float64).reshape(-1)
+        assert F_host.size == N * N
+        Fp = F_host.ctypes.data
+    rc = l.mgDistEmuRunCycleFile(os.fsencode(path), world, threshold, flags, Fp, U.ctypes.data, recs, max_recs, C.byref(res))
     if rc != 0:
         msg = l.mgLastError().decode()
         l.mgClearError()

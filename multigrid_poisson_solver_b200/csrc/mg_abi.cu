@@ -169,6 +169,7 @@ void mgShutdown(void)
     if (!c.ready) return;
     cudaStreamSynchronize(c.stream);
     cudaStreamSynchronize(c.comm_stream);
+    dist_release_on_shutdown();
     for (auto &kv : c.free_lists)
         for (void *p : kv.second) cudaFree(p);
     for (auto &kv : c.live) cudaFree(kv.first);
@@ -177,6 +178,7 @@ void mgShutdown(void)
     for (auto &kv : c.restrict_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.w); }
     for (auto &kv : c.prolong_tables) {
         cudaFree(kv.second.row_cell); cudaFree(kv.second.col_cell); cudaFree(kv.second.row_w); cudaFree(kv.second.col_w);
+        cudaFree(kv.second.row_info);
     }
     c.restrict_tables.clear();
     c.prolong_tables.clear();

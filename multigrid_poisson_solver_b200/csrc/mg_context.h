@@ -25,6 +25,7 @@ struct RestrictTable {
 struct ProlongTable {
     int *row_cell = nullptr, *col_cell = nullptr;
     double2 *row_w = nullptr, *col_w = nullptr;  // {lo_w, hi_w}
+    double4 *row_info = nullptr;                 // per fine row {lo_w, hi_w, cell (exact as a double), 0}: one 32-byte bulk copy per row
 };
 
 struct Context {

@@ -1,35 +1,43 @@
 // mg_dist.cu -- row-slab multi-GPU cycle driver.
 //
-// Fine levels are partitioned into contiguous row slabs, one per rank (one process per GPU);
-// every slab carries HALO extra rows on each side.  A fused pass needs the halo rows of its
-// input to be current; they are refreshed WHEN AN ARRAY IS PRODUCED: right behind every pass one
-// grouped send/recv carries the edge rows of its output (and of the restricted F_c) to both
-// neighbours, so no pass exchanges before it reads and a node costs one communication group.
-// The coarse partition is INDUCED by the fine one through the reference's floor map (a rank owns
-// the coarse rows whose lower fine row it owns), so restriction needs no communication at all and
-// prolongation only the coarse halo.  Levels below `threshold` rows are agglomerated on rank 0
-// (gather of F_c on the way down, scatter of U_c with halos on the way up) and handed as one
-// sub-cycle to the single-GPU interpreter; the other ranks idle there.
-// The smoothing error is the all-reduced sum of the slabs' red-parity sums (one collective per
-// batch of nodes; per sweep only in the trigger mode).
+// Fine levels are partitioned into contiguous row slabs, one per rank (one process per GPU); every
+// slab carries HALO extra rows on each side.  The halo rows of an array are refreshed WHEN THE ARRAY
+// IS PRODUCED and BY THE KERNEL THAT PRODUCES IT: the fused pass (k_strip) stores the rows a
+// neighbour keeps as its halo -- of the smoothed grid and of the restricted source -- straight into
+// the neighbour's slab through peer pointers (CUDA IPC over NVLink), while the rest of the same
+// launch sweeps the interior.  When the launch has drained, its last CTA publishes the pass number
+// in a flag word of each neighbour (st.release.sys); the neighbour's stream waits for that value
+// (cuStreamWaitValue32, no SM, no host) in front of its next pass.  There is no communication kernel,
+// no send/recv group and no extra stream on the data path.
 //
-// Transports of the row transfers: NCCL send/recv groups (default), or -- MG_DIST_TRANSPORT=staged --
-// copy engines writing into fixed staging buffers of the destination rank (opened once through CUDA
-// IPC) with sequence flags handled by stream memory operations: no SM is needed, so the exchange
-// really overlaps a persistent compute kernel (StagedTransport below).
+// The coarse partition is INDUCED by the fine one through the reference's floor map (a rank owns the
+// coarse rows whose lower fine row it owns), so restriction needs no communication beyond those
+// halo rows and prolongation only the coarse halo.  Levels below `threshold` rows are agglomerated:
+// at the boundary every rank broadcasts its share of the restricted grid to ALL ranks (peer stores
+// by a small copy kernel, flag per source rank), and every rank then runs the whole coarse sub-cycle
+// REDUNDANTLY with the single-GPU interpreter (fused nodes + coarse tail kernel).  All ranks end up
+// with the same coarse correction bit for bit, so the way up needs no scatter and nobody idles.
 //
-// Two communicators implement the same three primitives (point-to-point row transfers, scalar
-// all-reduce):
-//   EmuComm   all ranks live in this process on the current GPU (device-to-device copies).  It
+// Slabs, gather buffers and flags live in one ARENA per rank, cut by a deterministic bump allocator
+// that mirrors the level stack: every rank can compute every other rank's offsets, so one IPC
+// handle per rank (exchanged when the arena is created or grown, outside the timed region after the
+// first cycle) gives all peer pointers.
+//
+// The smoothing error is the all-reduced sum of the slabs' red-parity sums (one NCCL all-reduce per
+// batch of nodes; per sweep only in the trigger mode).  NCCL is otherwise used for the rendezvous
+// and for exchanging the IPC handles; it is bound at run time (dlopen of the libnccl.so.2 the host
+// program already loaded), so the library has no link-time NCCL dependency.
+//
+//   EmuComm   all ranks live in this process on the current GPU: the same arenas, peer stores, flags
+//             and stream waits, with every rank's passes queued in rank order on one stream.  It
 //             exists so the whole slab logic is testable bit-for-bit on one GPU.
-//   NcclComm  one rank per process; ncclSend/ncclRecv groups and ncclAllReduce on the library's
-//             stream.  NCCL is bound at run time (dlopen of the libnccl.so.2 the host program --
-//             e.g. torch -- already loaded), so the library has no link-time NCCL dependency.
+//   NcclComm  one rank per process.
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -49,43 +57,9 @@ namespace {
 
 constexpr int HALO = 8;           // >= S+2 for S <= 3 sweeps per pass, on the fine and (ratio >= 1.2) the coarse side
 constexpr double TRIGGER = 0.01;  // MG_solver_CPU.cpp:99
+constexpr int MAX_WORLD = 16;
 
-struct Xfer {                     // `count` doubles from src (valid on src_rank) to dst (valid on dst_rank)
-    int src_rank, dst_rank;
-    const double *src;
-    double *dst;
-    size_t count;
-};
-
-class Comm {
-public:
-    virtual ~Comm() {}
-    int world = 1;
-    std::vector<int> local;       // ranks living in this process
-    bool is_local(int r) const { return std::find(local.begin(), local.end(), r) != local.end(); }
-    // both primitives are queued on `stream`; one communicator must only ever be driven from ONE
-    // stream at a time (NCCL operations of a communicator may not run concurrently)
-    virtual void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) = 0;
-    // vals[i] = device pointer of local rank i; on return every one holds the sum over all ranks
-    virtual void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) = 0;
-};
-
-
-// ------------------------------------------------------------------ staged peer-to-peer transport
-// Row transfers without communication kernels.  Every rank owns a staging area with one slot per
-// (source rank, message parity) and a few 32-bit words: flag[src] (sequence number of the last
-// message src has delivered here), ack[dst] (last message of mine dst has consumed).  A message
-// from s to d is
-//     s:  wait  ack[d] >= seq - 2            (the slot of this parity is free again)
-//         copy  rows -> d.stage[s][seq & 1]   (peer write by a copy engine, over NVLink)
-//         write d.flag[s] = seq               (4-byte copy behind the data, same stream: ordered)
-//     d:  wait  flag[s] >= seq                (stream memory operation: no SM, no host)
-//         copy  stage[s][seq & 1] -> rows     (local)
-//         write s.ack[d] = seq
-// Sequence numbers are counted per ordered pair on both sides; every rank walks the same transfer
-// lists in the same order, so they agree without any handshake.  All sends of a call are queued
-// before its receives, hence no cycle of waits.  The staging areas of the other ranks are mapped
-// once (CUDA IPC when they live in other processes).
+// ---- driver entry points for stream memory operations
 struct DriverApi {
     CUresult (*WaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     CUresult (*WriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -103,151 +77,30 @@ struct DriverApi {
 };
 DriverApi g_drv;
 
-class StagedTransport {
+// ------------------------------------------------------------------ communicators
+// What is left to a communicator: the scalar all-reduce and the exchange of the arenas' IPC handles.
+class Comm {
 public:
-    static constexpr size_t CAP = 8u << 20;      // bytes per (source rank, parity) slot
-    struct Local {                                // one per rank living in this process
-        int rank = -1;
-        unsigned char *stage = nullptr;           // [world][2][CAP]
-        unsigned int *words = nullptr;            // flag[world] | ack[world] | scratch[2]
-        std::vector<unsigned char *> peer_stage;  // every rank's staging area as seen from here
-        std::vector<unsigned int *> peer_words;
-        std::vector<unsigned int> seq_out, seq_in;
-    };
-    int world = 0;
-    std::vector<Local> locals;
-    bool ready = false;
-
-    ~StagedTransport()
-    {
-        for (Local &l : locals) {
-            for (int q = 0; q < world; ++q) {
-                if (q == l.rank || ipc_opened.empty()) continue;
-                if (ipc_opened[q]) { cudaIpcCloseMemHandle(l.peer_stage[q]); cudaIpcCloseMemHandle(l.peer_words[q]); }
-            }
-            cudaFree(l.stage);
-            cudaFree(l.words);
-        }
-    }
-    std::vector<char> ipc_opened;                 // per rank: its areas were opened through IPC (one local rank only)
-
-    size_t words_count() const { return (size_t)2 * world + 2; }
-    bool add_local(int rank, int world_)
-    {
-        world = world_;
-        Local l;
-        l.rank = rank;
-        if (cudaMalloc(&l.stage, (size_t)world * 2 * CAP) != cudaSuccess) return false;
-        if (cudaMalloc(&l.words, words_count() * sizeof(unsigned int)) != cudaSuccess) return false;
-        if (cudaMemset(l.words, 0, words_count() * sizeof(unsigned int)) != cudaSuccess) return false;
-        l.peer_stage.assign((size_t)world, nullptr);
-        l.peer_words.assign((size_t)world, nullptr);
-        l.seq_out.assign((size_t)world, 0u);
-        l.seq_in.assign((size_t)world, 0u);
-        locals.push_back(l);
-        return true;
-    }
-    // all ranks in this process: the "peer" views are the other ranks' own pointers
-    bool link_in_process()
-    {
-        for (Local &a : locals)
-            for (Local &b : locals) { a.peer_stage[b.rank] = b.stage; a.peer_words[b.rank] = b.words; }
-        ready = g_drv.load();
-        return ready;
-    }
-    Local *local_of(int rank)
-    {
-        for (Local &l : locals) if (l.rank == rank) return &l;
-        return nullptr;
-    }
-    // same answer on every rank: it depends on the transfer sizes only
-    bool applicable(const std::vector<Xfer> &xs) const
-    {
-        if (!ready) return false;
-        std::map<std::pair<int, int>, size_t> bytes;
-        for (const Xfer &x : xs)
-            if (x.count && x.src_rank != x.dst_rank) bytes[{x.src_rank, x.dst_rank}] += x.count * sizeof(double);
-        for (const auto &kv : bytes) if (kv.second > CAP) return false;
-        return true;
-    }
-    void wait32(cudaStream_t st, unsigned int *addr, unsigned int value)
-    {
-        if (g_drv.WaitValue32((CUstream)st, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) fail(-36, "cuStreamWaitValue32");
-    }
-    // *remote = value, ordered behind everything queued on st so far (local scratch word, then a 4-byte copy)
-    void post32(cudaStream_t st, Local &l, int scratch, unsigned int *remote, unsigned int value)
-    {
-        unsigned int *w = l.words + 2 * world + scratch;
-        if (g_drv.WriteValue32((CUstream)st, (CUdeviceptr)w, value, 0) != CUDA_SUCCESS) fail(-36, "cuStreamWriteValue32");
-        check(cudaMemcpyAsync(remote, w, sizeof(unsigned int), cudaMemcpyDefault, st), "staged flag copy");
-    }
-    void transfer(const std::vector<Xfer> &xs, cudaStream_t st)
-    {
-        struct Item { const Xfer *x; size_t off; };
-        std::map<std::pair<int, int>, std::vector<Item>> groups;    // ordered: the same walk on every rank
-        std::map<std::pair<int, int>, size_t> fill;
-        for (const Xfer &x : xs) {
-            if (!x.count) continue;
-            if (x.src_rank == x.dst_rank) {
-                if (local_of(x.src_rank)) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, st), "self transfer");
-                continue;
-            }
-            size_t &off = fill[{x.src_rank, x.dst_rank}];
-            groups[{x.src_rank, x.dst_rank}].push_back({&x, off});
-            off += x.count * sizeof(double);
-        }
-        for (auto &kv : groups) {                  // ---- sends
-            const int s = kv.first.first, d = kv.first.second;
-            Local *l = local_of(s);
-            if (!l) continue;
-            const unsigned int seq = ++l->seq_out[d];
-            if (seq > 2) wait32(st, l->words + world + d, seq - 2);
-            unsigned char *slot = l->peer_stage[d] + ((size_t)s * 2 + (seq & 1u)) * CAP;
-            for (const Item &it : kv.second)
-                check(cudaMemcpyAsync(slot + it.off, it.x->src, it.x->count * sizeof(double), cudaMemcpyDefault, st), "staged send");
-            post32(st, *l, 0, l->peer_words[d] + s, seq);
-        }
-        for (auto &kv : groups) {                  // ---- receives
-            const int s = kv.first.first, d = kv.first.second;
-            Local *l = local_of(d);
-            if (!l) continue;
-            const unsigned int seq = ++l->seq_in[s];
-            wait32(st, l->words + s, seq);
-            const unsigned char *slot = l->stage + ((size_t)s * 2 + (seq & 1u)) * CAP;
-            for (const Item &it : kv.second)
-                check(cudaMemcpyAsync(it.x->dst, slot + it.off, it.x->count * sizeof(double), cudaMemcpyDeviceToDevice, st), "staged receive");
-            post32(st, *l, 1, l->peer_words[s] + world + d, seq);
-        }
-    }
+    virtual ~Comm() {}
+    int world = 1;
+    std::vector<int> local;       // ranks living in this process
+    bool is_local(int r) const { return std::find(local.begin(), local.end(), r) != local.end(); }
+    // vals[i] = device pointer of local rank i; on return every one holds the sum over all ranks (queued on `stream`)
+    virtual void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) = 0;
+    // every rank contributes `bytes` bytes; out = world x bytes in rank order (collective, synchronous); false on failure
+    virtual bool allgather_host(const void *mine, void *out, size_t bytes) = 0;
+    // min over all ranks of a host integer (collective, synchronous): agreement on success / failure
+    virtual int allreduce_min_host(int v) = 0;
 };
-
-bool staged_requested()
-{
-    const char *e = getenv("MG_DIST_TRANSPORT");
-    return e && strcmp(e, "staged") == 0;
-}
 
 class EmuComm : public Comm {
 public:
-    std::unique_ptr<StagedTransport> staged;      // MG_DIST_TRANSPORT=staged: the protocol of the real transport, in one process
     explicit EmuComm(int g)
     {
         world = g;
         for (int r = 0; r < g; ++r) local.push_back(r);
-        if (g > 1 && staged_requested()) {
-            staged.reset(new StagedTransport());
-            bool good = true;
-            for (int r = 0; r < g && good; ++r) good = staged->add_local(r, g);
-            if (!good || !staged->link_in_process()) { staged.reset(); fail(-37, "staged transport: set-up failed"); }
-        }
     }
     ~EmuComm() override { cudaDeviceSynchronize(); }
-    void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) override
-    {
-        if (staged && staged->applicable(xs)) { staged->transfer(xs, stream); return; }
-        for (const Xfer &x : xs)
-            if (x.count) check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, stream), "emu transfer");
-    }
     void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) override
     {
         std::vector<double> acc((size_t)n, 0.0), tmp((size_t)n);
@@ -258,6 +111,8 @@ public:
         }
         for (double *v : vals) check(cudaMemcpy(v, acc.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice), "emu allreduce H2D");
     }
+    bool allgather_host(const void *, void *, size_t) override { return true; }   // (all ranks are local: nothing to exchange)
+    int allreduce_min_host(int v) override { return v; }
 };
 
 // ---- NCCL bound at run time
@@ -266,12 +121,8 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load()
     {
@@ -281,8 +132,7 @@ struct NcclApi {
         if (!handle) { fail(-30, std::string("cannot load libnccl.so.2: ") + dlerror()); return false; }
 #define MG_SYM(field, name) field = (decltype(field))dlsym(handle, name); if (!field) { fail(-31, "libnccl.so.2 lacks " name); return false; }
         MG_SYM(GetUniqueId, "ncclGetUniqueId") MG_SYM(CommInitRank, "ncclCommInitRank") MG_SYM(CommDestroy, "ncclCommDestroy")
-        MG_SYM(Send, "ncclSend") MG_SYM(Recv, "ncclRecv") MG_SYM(AllReduce, "ncclAllReduce") MG_SYM(AllGather, "ncclAllGather") MG_SYM(GroupStart, "ncclGroupStart")
-        MG_SYM(GroupEnd, "ncclGroupEnd") MG_SYM(GetErrorString, "ncclGetErrorString")
+        MG_SYM(AllReduce, "ncclAllReduce") MG_SYM(AllGather, "ncclAllGather") MG_SYM(GetErrorString, "ncclGetErrorString")
 #undef MG_SYM
         return true;
     }
@@ -293,85 +143,51 @@ class NcclComm : public Comm {
 public:
     ncclComm_t comm = nullptr;
     int rank = 0;
+    unsigned char *stage = nullptr;   // device staging of the host collectives
+    size_t stage_bytes = 0;
     bool ok(ncclResult_t r, const char *what)
     {
         if (r == ncclSuccess) return true;
         fail(-32, std::string(what) + ": " + g_nccl.GetErrorString(r));
         return false;
     }
-    std::unique_ptr<StagedTransport> staged;      // MG_DIST_TRANSPORT=staged
-
-    // Collective: every rank allocates its staging area, the IPC handles are all-gathered, every rank
-    // maps the others' areas, and the transport is switched on only if ALL ranks succeeded.
-    bool setup_staged()
+    ~NcclComm() override { cudaFree(stage); }
+    bool reserve(size_t bytes)               // staging of allgather_host; called once at init so that no collective can fail on memory later
     {
-        struct Pack { cudaIpcMemHandle_t stage, words; };
-        cudaStream_t st = ctx().stream;
-        std::unique_ptr<StagedTransport> t(new StagedTransport());
-        int good = (t->add_local(rank, world) && g_drv.load()) ? 1 : 0;
-        Pack mine;
-        memset(&mine, 0, sizeof mine);
-        if (good) {
-            StagedTransport::Local &l = t->locals[0];
-            good = cudaIpcGetMemHandle(&mine.stage, l.stage) == cudaSuccess && cudaIpcGetMemHandle(&mine.words, l.words) == cudaSuccess;
-        }
-        unsigned char *dsend = nullptr, *drecv = nullptr;
-        int *dflag = nullptr;
-        std::vector<Pack> packs((size_t)world);
-        bool coll = cudaMalloc(&dsend, sizeof(Pack)) == cudaSuccess && cudaMalloc(&drecv, (size_t)world * sizeof(Pack)) == cudaSuccess &&
-                    cudaMalloc(&dflag, sizeof(int)) == cudaSuccess;
-        if (!coll) { fail(-37, "staged transport: cudaMalloc"); return false; }
-        cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice);
-        coll = ok(g_nccl.AllGather(dsend, drecv, sizeof(Pack), ncclChar, comm, st), "ncclAllGather (IPC handles)");
-        cudaStreamSynchronize(st);
-        cudaMemcpy(packs.data(), drecv, (size_t)world * sizeof(Pack), cudaMemcpyDeviceToHost);
-        if (good && coll) {
-            StagedTransport::Local &l = t->locals[0];
-            t->ipc_opened.assign((size_t)world, 0);
-            l.peer_stage[rank] = l.stage;
-            l.peer_words[rank] = l.words;
-            for (int q = 0; q < world && good; ++q) {
-                if (q == rank) continue;
-                void *a = nullptr, *b = nullptr;
-                good = cudaIpcOpenMemHandle(&a, packs[q].stage, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
-                       cudaIpcOpenMemHandle(&b, packs[q].words, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-                if (good) { l.peer_stage[q] = (unsigned char *)a; l.peer_words[q] = (unsigned int *)b; t->ipc_opened[q] = 1; }
-            }
-            if (!good) cudaGetLastError();
-        }
-        int all = (good && coll) ? 1 : 0;
-        cudaMemcpy(dflag, &all, sizeof(int), cudaMemcpyHostToDevice);
-        ok(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, comm, st), "ncclAllReduce (staged transport)");
-        cudaStreamSynchronize(st);
-        cudaMemcpy(&all, dflag, sizeof(int), cudaMemcpyDeviceToHost);
-        cudaFree(dsend); cudaFree(drecv); cudaFree(dflag);
-        if (all) {
-            t->ready = true;
-            staged = std::move(t);
-            if (rank == 0 && getenv("MG_DIST_TRACE")) fprintf(stderr, "[mg trace] staged transport ready on %d ranks (CUDA IPC)\n", world);
-        }
-        else if (rank == 0) fprintf(stderr, "[ WARNING ]: staged transport unavailable on some rank; using NCCL send/recv\n");
-        return all != 0;
-    }
-
-    void transfer(const std::vector<Xfer> &xs, cudaStream_t stream) override
-    {
-        if (staged && staged->applicable(xs)) { staged->transfer(xs, stream); return; }
-        ok(g_nccl.GroupStart(), "ncclGroupStart");
-        for (const Xfer &x : xs) {
-            if (!x.count) continue;
-            if (x.src_rank == rank && x.dst_rank == rank) {
-                check(cudaMemcpyAsync(x.dst, x.src, x.count * sizeof(double), cudaMemcpyDeviceToDevice, stream), "self transfer");
-                continue;
-            }
-            if (x.src_rank == rank) ok(g_nccl.Send(x.src, x.count, ncclDouble, x.dst_rank, comm, stream), "ncclSend");
-            if (x.dst_rank == rank) ok(g_nccl.Recv(x.dst, x.count, ncclDouble, x.src_rank, comm, stream), "ncclRecv");
-        }
-        ok(g_nccl.GroupEnd(), "ncclGroupEnd");
+        if (bytes <= stage_bytes) return true;
+        cudaFree(stage);
+        stage = nullptr;
+        stage_bytes = 0;
+        if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+        stage_bytes = bytes;
+        return true;
     }
     void allreduce_sum(const std::vector<double *> &vals, int n, cudaStream_t stream) override
     {
         ok(g_nccl.AllReduce(vals[0], vals[0], (size_t)n, ncclDouble, ncclSum, comm, stream), "ncclAllReduce");
+    }
+    // NOTE: a host collective is always entered, whatever failed locally before (a rank that returned early would leave
+    // the others blocked inside NCCL): local failure travels as data through allreduce_min_host.
+    bool allgather_host(const void *mine, void *out, size_t bytes) override
+    {
+        cudaStream_t st = ctx().stream;
+        if ((size_t)(world + 1) * bytes > stage_bytes) { fail(-39, "slab driver: host collective larger than its staging buffer"); return false; }
+        cudaMemcpyAsync(stage, mine, bytes, cudaMemcpyHostToDevice, st);
+        const bool sent = ok(g_nccl.AllGather(stage, stage + bytes, bytes, ncclChar, comm, st), "ncclAllGather");
+        cudaStreamSynchronize(st);
+        if (sent) cudaMemcpy(out, stage + bytes, (size_t)world * bytes, cudaMemcpyDeviceToHost);
+        return sent;
+    }
+    int allreduce_min_host(int v) override
+    {
+        cudaStream_t st = ctx().stream;
+        int *d = (int *)(ctx().dev_scalar + 8);
+        cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, st);
+        ok(g_nccl.AllReduce(d, d, 1, ncclInt, ncclMin, comm, st), "ncclAllReduce (min)");
+        cudaStreamSynchronize(st);
+        int out = 0;
+        cudaMemcpy(&out, d, sizeof(int), cudaMemcpyDeviceToHost);
+        return out;
     }
 };
 std::unique_ptr<NcclComm> g_nccl_comm;
@@ -448,7 +264,7 @@ bool induce_geometry(const LevelGeom &fine, int M, int world, int threshold, Lev
     coarse.bound.clear();
     if (!fine.dist) return true;
     if (!pair_fusable_host(fine.N, M)) { why = "a distributed level needs an even size and a fusable transfer pair"; return false; }
-    if (!(world > 1 && M >= threshold)) return true;
+    if (!(world > 1 && M >= threshold && M % 2 == 0)) return true;
     const std::vector<int> b = coarse_bounds(fine, M, world);
     for (int k = 0; k < world; ++k)
         if (b[k + 1] - b[k] < 2 * HALO) return true;   // slabs too thin for single-neighbour halos: agglomerate
@@ -468,123 +284,225 @@ Slab slab_of(const LevelGeom &g, int rank)
     return s;
 }
 
-struct RankLevel {            // one rank's share of one level
+size_t slab_bytes(const LevelGeom &g, int rank)
+{
+    const Slab s = slab_of(g, rank);
+    return ((size_t)s.rows * g.N * sizeof(double) + 255) / 256 * 256;
+}
+
+// ------------------------------------------------------------------ the fabric: arenas + flag words of all ranks
+// Flag words of a rank (unsigned int): [0] pass number published by the rank below, [1] by the rank above,
+// [2 + s] gather number published by source rank s, [2 + MAX_WORLD] set when a peer gave up (error).
+constexpr int W_FROM_LO = 0, W_FROM_HI = 1, W_GATHER = 2, W_ABORT = 2 + MAX_WORLD, N_WORDS = 64;
+
+__global__ void k_peer_bcast(const double *src, size_t count, int n_dst, const double *const *dst_table, unsigned int *const *flag_table,
+                             unsigned int flag_val, unsigned int *ticket)
+{
+    // every destination gets the same `count` doubles at its own address; 16-byte vectors when everything is aligned
+    __shared__ bool last;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int d = 0; d < n_dst; ++d) {
+        double *dst = const_cast<double *>(dst_table[d]);
+        if ((((size_t)src | (size_t)dst) & 15) == 0) {
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 *d2 = reinterpret_cast<double2 *>(dst);
+            for (size_t k = t0; k < count / 2; k += stride) d2[k] = s2[k];
+            if ((count & 1) && t0 == 0) dst[count - 1] = src[count - 1];
+        } else {
+            for (size_t k = t0; k < count; k += stride) dst[k] = src[k];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int d = 0; d < n_dst; ++d) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_table[d]), "r"(flag_val) : "memory");
+        *ticket = 0u;
+    }
+}
+
+// one warp: lane s waits until source rank s has published gather number >= want (or a peer aborted)
+__global__ void k_wait_gather(const unsigned int *words, int world, int self, unsigned int want)
+{
+    const int s = threadIdx.x;
+    if (s >= world || s == self) return;
+    const unsigned int *w = words + W_GATHER + s, *abort_w = words + W_ABORT;
+    for (;;) {
+        unsigned int v, a;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+        if ((int)(v - want) >= 0) break;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(abort_w) : "memory");
+        if (a) break;
+        __nanosleep(200);
+    }
+}
+
+struct PeerView {             // one rank's arena and flag words as seen from this process
+    unsigned char *arena = nullptr;
+    unsigned int *words = nullptr;
+    bool arena_ipc = false, words_ipc = false;
+};
+
+class Fabric {
+public:
+    Comm &comm;
+    int world;
+    std::vector<PeerView> peer;            // [world]
+    size_t cap = 0;                        // bytes of every rank's arena
+    size_t gather_bytes = 0;               // size of ONE gather buffer (two of them sit at the bottom of every arena)
+    std::vector<size_t> top;               // [world] bump pointers (identical bookkeeping in every process)
+    unsigned int seq = 0;                  // distributed passes launched so far (the same on every rank)
+    unsigned int gathers = 0;              // agglomeration gathers so far
+    bool ok = false;
+    // device tables of the broadcast kernel, one set per local rank
+    struct Tables {                        // per gather parity: device arrays + the host copy they were filled from
+        const double **dst[2] = {nullptr, nullptr};
+        unsigned int **flag[2] = {nullptr, nullptr};
+        const double *dst_h[2][MAX_WORLD] = {};
+        unsigned int *flag_h[2][MAX_WORLD] = {};
+    };
+    std::vector<Tables> tables;            // [local index]
+
+    explicit Fabric(Comm &c) : comm(c), world(c.world), peer((size_t)c.world), top((size_t)c.world, 0)
+    {
+        ok = g_drv.load() && world <= MAX_WORLD;
+        if (!ok) { fail(-36, "slab driver: cuStreamWaitValue32 is unavailable (or more than 16 ranks)"); return; }
+        // flag words: allocated once, zeroed, exchanged once
+        for (int r : comm.local) {
+            unsigned int *w = nullptr;
+            if (cudaMalloc(&w, N_WORDS * sizeof(unsigned int)) != cudaSuccess || cudaMemset(w, 0, N_WORDS * sizeof(unsigned int)) != cudaSuccess) ok = false;
+            peer[r].words = w;
+        }
+        tables.resize(comm.local.size());
+        for (auto &t : tables)
+            for (int k = 0; k < 2; ++k)
+                if (cudaMalloc(&t.dst[k], MAX_WORLD * sizeof(double *)) != cudaSuccess || cudaMalloc(&t.flag[k], MAX_WORLD * sizeof(unsigned int *)) != cudaSuccess) ok = false;
+        cudaDeviceSynchronize();
+        ok = exchange(false) && ok;
+    }
+    ~Fabric() { release(true); }
+    Fabric(const Fabric &) = delete;
+    Fabric &operator=(const Fabric &) = delete;
+
+    void release(bool words_too)
+    {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < world; ++r) {
+            PeerView &p = peer[r];
+            if (p.arena) { if (p.arena_ipc) cudaIpcCloseMemHandle(p.arena); else if (comm.is_local(r)) cudaFree(p.arena); }
+            p.arena = nullptr;
+            p.arena_ipc = false;
+            if (words_too && p.words) {
+                if (p.words_ipc) cudaIpcCloseMemHandle(p.words); else if (comm.is_local(r)) cudaFree(p.words);
+                p.words = nullptr;
+                p.words_ipc = false;
+            }
+        }
+        if (words_too)
+            for (auto &t : tables)
+                for (int k = 0; k < 2; ++k) { cudaFree(t.dst[k]); cudaFree(t.flag[k]); t.dst[k] = nullptr; t.flag[k] = nullptr; }
+        cap = 0;
+    }
+
+    // Collective: publish the local arena (arenas == true) or flag words to the other processes and map theirs.
+    bool exchange(bool arenas)
+    {
+        if (comm.local.size() == (size_t)world) return true;            // all ranks in this process: the pointers are shared already
+        const int me = comm.local[0];
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof mine);
+        void *ptr = arenas ? (void *)peer[me].arena : (void *)peer[me].words;
+        int good = ptr && cudaIpcGetMemHandle(&mine, ptr) == cudaSuccess ? 1 : 0;
+        std::vector<cudaIpcMemHandle_t> all((size_t)world);
+        good = comm.allgather_host(&mine, all.data(), sizeof mine) && good;
+        good = comm.allreduce_min_host(good);                            // every rank has a handle to offer
+        if (good) {
+            for (int q = 0; q < world && good; ++q) {
+                if (q == me) continue;
+                void *m = nullptr;
+                if (cudaIpcOpenMemHandle(&m, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = 0; cudaGetLastError(); break; }
+                if (arenas) { peer[q].arena = (unsigned char *)m; peer[q].arena_ipc = true; }
+                else { peer[q].words = (unsigned int *)m; peer[q].words_ipc = true; }
+            }
+        }
+        good = comm.allreduce_min_host(good);                            // ... and every rank mapped all of them
+        if (!good) fail(-37, "slab driver: CUDA IPC mapping of the peer arenas failed (peer access over NVLink is required)");
+        return good != 0;
+    }
+
+    // Collective: arenas of at least `need` bytes (the same number on every rank).  Keeps the current ones when large enough.
+    bool reserve(size_t need, size_t gather_need)
+    {
+        if (!ok) return false;
+        if (need <= cap && gather_need <= gather_bytes) return true;
+        release(false);
+        gather_bytes = std::max(gather_bytes, gather_need);
+        const size_t want = std::max(need, (size_t)1 << 20);
+        int good = 1;
+        for (int r : comm.local) {
+            void *a = nullptr;
+            if (cudaMalloc(&a, want) != cudaSuccess) { good = 0; cudaGetLastError(); }
+            peer[r].arena = (unsigned char *)a;
+        }
+        good = comm.allreduce_min_host(good);
+        if (!good) { fail(-38, "slab driver: cannot allocate the slab arena"); ok = false; return false; }
+        cap = want;
+        ok = exchange(true);
+        return ok;
+    }
+
+    // ---- bump allocation, the same in every process: `bytes[r]` from rank r's arena; returns the offsets
+    std::vector<size_t> alloc(const std::vector<size_t> &bytes)
+    {
+        std::vector<size_t> off((size_t)world);
+        for (int r = 0; r < world; ++r) { off[r] = top[r]; top[r] += bytes[r]; }
+        return off;
+    }
+    template <class T>
+    T *at(int rank, size_t off) const { return reinterpret_cast<T *>(peer[rank].arena + off); }
+    size_t gather_off(unsigned int g) const { return (size_t)(g & 1u) * gather_bytes; }   // double-buffered by gather parity
+
+    void wait32(cudaStream_t st, unsigned int *addr, unsigned int value)
+    {
+        if (g_drv.WaitValue32((CUstream)st, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) fail(-36, "cuStreamWaitValue32");
+    }
+    // Tell every peer that this rank gives up (their flag waits pass, their gather waits end): called on a local error so
+    // that the other ranks come back with an error instead of hanging.
+    void abort_peers(cudaStream_t st)
+    {
+        for (int me : comm.local)
+            for (int q = 0; q < world; ++q) {
+                if (q == me || !peer[q].words) continue;
+                g_drv.WriteValue32((CUstream)st, (CUdeviceptr)(peer[q].words + W_ABORT), 1u, 0);
+                if (q == me - 1) g_drv.WriteValue32((CUstream)st, (CUdeviceptr)(peer[q].words + W_FROM_HI), 0x7fffffffu, 0);
+                if (q == me + 1) g_drv.WriteValue32((CUstream)st, (CUdeviceptr)(peer[q].words + W_FROM_LO), 0x7fffffffu, 0);
+            }
+    }
+};
+
+struct RankLevel {            // one local rank's share of one level
     Slab slab;
-    bool present = false;     // dist: every rank; agglomerated: rank 0 only
     double *U = nullptr, *W = nullptr, *F = nullptr;
-    bool owns_F = true;
+    bool owns_F = true;       // agglomerated levels: F from the pool (false: the gather buffer / the caller's source)
+    bool pooled = false;      // agglomerated level: U, W (and F if owns_F) come from the pool
+};
+
+struct LevelAlloc {           // arena offsets of a distributed level, for EVERY rank
+    std::vector<size_t> U, W, F;
+    std::vector<size_t> saved_top;
 };
 
 struct RankState {
     int rank = 0;
     std::vector<RankLevel> lv;
-    double *scal = nullptr;   // device scalars: [0] error partial, [1] final abs-diff partial
-};
-
-// Halo rows of one array of a distributed level: rank k's last HALO owned rows go to rank k+1's
-// lower halo, rank k+1's first HALO owned rows to rank k's upper halo.  ptr(rank) = base of that
-// rank's local array (nullptr when the rank lives in another process).
-template <class Ptr>
-void halo_xfers(const LevelGeom &g, const Comm &comm, Ptr ptr, std::vector<Xfer> &xs)
-{
-    if (!g.dist) return;
-    const size_t N = g.N;
-    for (int k = 0; k + 1 < comm.world; ++k) {
-        if (!comm.is_local(k) && !comm.is_local(k + 1)) continue;
-        const Slab a = slab_of(g, k), b = slab_of(g, k + 1);
-        double *pa = ptr(k), *pb = ptr(k + 1);
-        const int up_lo = std::max(a.own_hi - HALO, b.row0);
-        xs.push_back({k, k + 1, pa ? pa + (size_t)(up_lo - a.row0) * N : nullptr, pb ? pb + (size_t)(up_lo - b.row0) * N : nullptr,
-                      (size_t)(a.own_hi - up_lo) * N});
-        const int dn_hi = std::min(b.own_lo + HALO, a.row0 + a.rows);
-        xs.push_back({k + 1, k, pb ? pb + (size_t)(b.own_lo - b.row0) * N : nullptr, pa ? pa + (size_t)(b.own_lo - a.row0) * N : nullptr,
-                      (size_t)(dn_hi - b.own_lo) * N});
-    }
-}
-
-// Stream protocol of the slab driver.  Kernels run on the compute stream `ms`; EVERY communication
-// primitive (halo exchange, gather/scatter, all-reduce, the scalar read-backs that follow an
-// all-reduce) is queued on the communication stream `cs`, so the communicator sees one ordered
-// stream.  A pass is launched in two parts: the edge row segments first -- they produce the rows
-// the neighbours' halos need -- then the interior; the halo exchange of the pass OUTPUT is queued
-// on cs behind the edge launch and runs while the interior launch computes.  The next pass waits
-// for that exchange (wait_halo) before it starts.  Because halos are refreshed when an array is
-// produced, no pass ever has to exchange before it reads.
-// Opt-in (MG_DIST_OVERLAP=1): measured on 2 x B200 it does not pay with NCCL transfers -- NCCL's
-// send/recv kernels need SMs, and the persistent interior launch holds every SM until it ends, so
-// the exchange starts late anyway.  By default both streams are the compute stream
-// and passes are launched whole, the exchange of the output right behind them.
-struct TwoStream {
-    cudaStream_t ms = nullptr, cs = nullptr, cs_hi = nullptr;   // cs: where communication goes right now (cs_hi or ms)
-    cudaEvent_t ev_join = nullptr, ev_edge = nullptr, ev_halo = nullptr;
-    bool overlap = true, halo_pending = false;
-    long long min_points = 0;   // slabs smaller than this run their communication in line on ms (MG_DIST_OVERLAP_MIN_POINTS)
-    TwoStream()
-    {
-        ms = ctx().stream;
-        cs_hi = ctx().comm_stream;
-        const char *e = getenv("MG_DIST_OVERLAP");
-        overlap = e && atoi(e) != 0;
-        if ((e = getenv("MG_DIST_OVERLAP_MIN_POINTS"))) min_points = atoll(e);
-        cs = overlap ? cs_hi : ms;
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_edge, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming);
-    }
-    ~TwoStream()
-    {
-        sync();
-        cudaEventDestroy(ev_join); cudaEventDestroy(ev_edge); cudaEventDestroy(ev_halo);
-    }
-    TwoStream(const TwoStream &) = delete;
-    TwoStream &operator=(const TwoStream &) = delete;
-    // communication queued after this sees everything the compute stream has been given so far
-    void to_comm()
-    {
-        if (cs == ms) return;
-        cudaEventRecord(ev_join, ms);
-        cudaStreamWaitEvent(cs, ev_join, 0);
-    }
-    // kernels queued after this see every communication queued so far
-    void to_compute()
-    {
-        halo_pending = false;
-        if (cs == ms) return;
-        cudaEventRecord(ev_join, cs);
-        cudaStreamWaitEvent(ms, ev_join, 0);
-    }
-    void halo_posted() { cudaEventRecord(ev_halo, cs); halo_pending = true; }
-    void wait_halo()
-    {
-        if (halo_pending && cs != ms) cudaStreamWaitEvent(ms, ev_halo, 0);
-        halo_pending = false;
-    }
-    void edge_done()   // the exchange queued next may start as soon as the edge launch has finished
-    {
-        if (cs == ms) return;
-        cudaEventRecord(ev_edge, ms);
-        cudaStreamWaitEvent(cs, ev_edge, 0);
-    }
-    void sync()
-    {
-        check(cudaStreamSynchronize(ms), "sync");
-        check(cudaStreamSynchronize(cs_hi), "sync (comm)");
-        halo_pending = false;
-    }
-    // choose where the communication of the next pass goes: overlapped on cs_hi, or in line on ms
-    // (small levels: the cross-stream hand-offs cost more than the exchange they would hide)
-    void select(bool overlapped)
-    {
-        cudaStream_t want = (overlap && overlapped) ? cs_hi : ms;
-        if (want == cs) return;
-        if (cs != ms) to_compute();   // leaving cs_hi: ms continues behind everything queued there
-        cs = want;                    // entering cs_hi: every primitive there starts with to_comm()/edge_done()
-    }
+    double *scal = nullptr;   // device scalars: error partials of the batch, [60] final abs-diff partial
 };
 
 class DistCycle {
 public:
-    DistCycle(Comm &c, int threshold) : comm(c), threshold_(threshold)
+    DistCycle(Comm &c, Fabric &f, int threshold) : comm(c), fab(f), threshold_(threshold)
     {
         for (int r : comm.local) {
             RankState st;
@@ -592,35 +510,54 @@ public:
             st.scal = (double *)pool_alloc(64 * sizeof(double));
             ranks.push_back(st);
         }
+        std::fill(fab.top.begin(), fab.top.end(), 2 * fab.gather_bytes);   // the two gather buffers sit at the bottom
     }
     ~DistCycle()
     {
-        ts.sync();                               // nothing queued may outlive the buffers
+        cudaStreamSynchronize(ctx().stream);     // nothing queued may outlive the buffers
         while (!geom.empty()) pop();
         for (auto &st : ranks) pool_free(st.scal);
     }
 
     Comm &comm;
+    Fabric &fab;
     int threshold_;
     std::vector<LevelGeom> geom;
+    std::vector<LevelAlloc> alloc;
     std::vector<RankState> ranks;
     int init_ = 1;
-    TwoStream ts;
     int scal_used_ = 0;         // slots of the ranks' scal arrays holding error sums of this batch
 
-    void push(const LevelGeom &g, double *borrowed_F = nullptr)
+    // borrowed_F: the top level's source slab of local rank 0 (single local rank only); gathered: F is the gather buffer
+    void push(const LevelGeom &g, double *borrowed_F = nullptr, bool gathered = false, unsigned int gather_no = 0)
     {
         geom.push_back(g);
+        LevelAlloc a;
+        a.saved_top = fab.top;
+        if (g.dist) {
+            std::vector<size_t> bytes((size_t)comm.world);
+            for (int r = 0; r < comm.world; ++r) bytes[r] = slab_bytes(g, r);
+            a.U = fab.alloc(bytes);
+            a.W = fab.alloc(bytes);
+            if (!borrowed_F) a.F = fab.alloc(bytes);
+        }
+        alloc.push_back(a);
         for (auto &st : ranks) {
             RankLevel l;
             l.slab = slab_of(g, st.rank);
-            l.present = g.dist || st.rank == 0;
-            if (l.present) {
-                const size_t bytes = (size_t)l.slab.rows * g.N * sizeof(double);
+            if (g.dist) {
+                l.U = fab.at<double>(st.rank, a.U[st.rank]);
+                l.W = fab.at<double>(st.rank, a.W[st.rank]);
+                l.F = borrowed_F ? borrowed_F : fab.at<double>(st.rank, a.F[st.rank]);
+                l.owns_F = false;
+            } else {
+                const size_t bytes = (size_t)g.N * g.N * sizeof(double);
+                l.pooled = true;
                 l.U = (double *)pool_alloc(bytes);
                 l.W = (double *)pool_alloc(bytes);
-                l.F = borrowed_F ? borrowed_F : (double *)pool_alloc(bytes);
-                l.owns_F = borrowed_F == nullptr;
+                if (gathered) { l.F = fab.at<double>(st.rank, fab.gather_off(gather_no)); l.owns_F = false; }
+                else if (borrowed_F) { l.F = borrowed_F; l.owns_F = false; }
+                else l.F = (double *)pool_alloc(bytes);
             }
             st.lv.push_back(l);
         }
@@ -629,85 +566,123 @@ public:
     {
         for (auto &st : ranks) {
             RankLevel &l = st.lv.back();
-            pool_free(l.U); pool_free(l.W);
-            if (l.owns_F) pool_free(l.F);
+            if (l.pooled) {
+                pool_free(l.U); pool_free(l.W);
+                if (l.owns_F) pool_free(l.F);
+            }
             st.lv.pop_back();
         }
+        fab.top = alloc.back().saved_top;
+        alloc.pop_back();
         geom.pop_back();
         if (geom.size() == 1) init_ = 0;
     }
     bool restart_top() const { return init_ == 0 && geom.size() == 1; }
 
-    // coarse geometry induced by the fine one (see the header comment)
     bool induce(const LevelGeom &fine, int M, LevelGeom &coarse, std::string &why)
     {
         return induce_geometry(fine, M, comm.world, threshold_, coarse, why);
     }
 
-    // ---- halo transfers of one array of level `li` (which: 0 U, 1 F, 2 W)
-    void add_halo(int li, int which, std::vector<Xfer> &xs)
-    {
-        halo_xfers(geom[li], comm, [&](int rank) -> double * {
-            for (auto &st : ranks)
-                if (st.rank == rank) return which == 0 ? st.lv[li].U : which == 1 ? st.lv[li].F : st.lv[li].W;
-            return nullptr;
-        }, xs);
-    }
-
-    // sum the ranks' partials at scal[idx .. idx+n); every local rank ends with the global sums (on ts.cs)
+    // sum the ranks' partials at scal[idx .. idx+n); every local rank ends with the global sums
     void allreduce(int idx, int n = 1)
     {
-        ts.to_comm();
         if (comm.world == 1) return;
         std::vector<double *> v;
         for (auto &st : ranks) v.push_back(st.scal + idx);
-        comm.allreduce_sum(v, n, ts.cs);
+        comm.allreduce_sum(v, n, ctx().stream);
     }
 
-    // gather / scatter between rank 0 and the slabs: compute -> comm -> compute
-    void transfer_now(const std::vector<Xfer> &xs)
-    {
-        ts.to_comm();
-        comm.transfer(xs, ts.cs);
-        ts.to_compute();
-    }
-
-    // One fused pass over every local slab of distributed level `li`: S sweeps from U (in_mode 0),
-    // from zero (1) or from U + prolongation of the coarse slabs `uc` (2); optional red-parity error
-    // sum into scal[scal_idx]; optional restriction of the negated residual into `fc`.  The output
-    // (W, then swapped into U) and, with fc_halo, the coarse source get their halos refreshed by an
-    // exchange that overlaps the interior part of the pass.
-    void pass(int li, double L, int S, int in_mode, bool want_err, int scal_idx, int M, const std::vector<double *> &fc,
-              const std::vector<Slab> &fc_slab, bool fc_halo, int Nc, const std::vector<const double *> &uc,
+    // One fused pass over every local slab of distributed level `li`: S sweeps from U (in_mode 0), from zero (1) or
+    // from U + prolongation of the coarse grid `uc` (2); optional red-parity error sum into scal[scal_idx]; optional
+    // restriction of the negated residual into `fc` (the coarse level li+1: its slabs when fc_dist, else every rank's
+    // full gather buffer).  The rows the neighbours keep as halos -- of the output W and of a distributed F_c -- go
+    // straight into their arenas; the pass number is published when the launch has drained.
+    void pass(int li, double L, int S, int in_mode, bool want_err, int scal_idx, int M, bool with_fc, bool fc_dist,
+              const std::vector<int> &cb, const std::vector<double *> &fc_full, int Nc, const std::vector<const double *> &uc,
               const std::vector<Slab> &uc_slab)
     {
         const LevelGeom &g = geom[li];
         const bool writes_U = !(S == 0 && in_mode == 0);
-        // the edge segments hold >= 24 fine rows per side: enough for 8 coarse halo rows up to ratio 2.5
-        ts.select((long long)g.N * (g.N / comm.world) >= ts.min_points);
-        const bool split = ts.cs != ts.ms && (!fc_halo || (double)(g.N - 1) <= 2.5 * (double)(M - 1));
-        auto launch = [&](int subset) {
-            for (size_t i = 0; i < ranks.size(); ++i) {
-                RankLevel &l = ranks[i].lv[li];
-                slab_pass(g.N, L, S, in_mode, l.U, l.F, writes_U ? l.W : nullptr, l.slab, want_err, ranks[i].scal + scal_idx, M,
-                          fc.empty() ? nullptr : fc[i], fc.empty() ? nullptr : &fc_slab[i], Nc, uc.empty() ? nullptr : uc[i],
-                          uc.empty() ? nullptr : &uc_slab[i], subset);
+        const unsigned int prev = fab.seq, mine = ++fab.seq;
+        cudaStream_t st_ = ctx().stream;
+        for (size_t i = 0; i < ranks.size(); ++i) {
+            const int r = ranks[i].rank;
+            RankLevel &l = ranks[i].lv[li];
+            PeerLinks pl;
+            // the previous pass of both neighbours has drained: my halos are current, and nobody still reads what I overwrite
+            if (r > 0) fab.wait32(st_, fab.peer[r].words + W_FROM_LO, prev);
+            if (r + 1 < comm.world) fab.wait32(st_, fab.peer[r].words + W_FROM_HI, prev);
+            pl.flag_val = mine;
+            if (r > 0) pl.flag_lo = fab.peer[r - 1].words + W_FROM_HI;
+            if (r + 1 < comm.world) pl.flag_hi = fab.peer[r + 1].words + W_FROM_LO;
+            if (writes_U) {
+                if (r > 0) pl.U_lo = fab.at<double>(r - 1, alloc[li].W[r - 1]) - (ptrdiff_t)slab_of(g, r - 1).row0 * g.N;
+                if (r + 1 < comm.world) pl.U_hi = fab.at<double>(r + 1, alloc[li].W[r + 1]) - (ptrdiff_t)slab_of(g, r + 1).row0 * g.N;
+                pl.u_lo_end = l.slab.own_lo + HALO;
+                pl.u_hi_begin = l.slab.own_hi - HALO;
             }
-        };
-        auto post_halo = [&]() {
-            std::vector<Xfer> xs;
-            if (writes_U) add_halo(li, 2, xs);
-            if (fc_halo) add_halo(li + 1, 1, xs);
-            if (xs.empty()) return;
-            ts.edge_done();
-            comm.transfer(xs, ts.cs);
-            ts.halo_posted();
-        };
-        ts.wait_halo();
-        if (split) { launch(1); post_halo(); launch(2); }
-        else       { launch(0); post_halo(); }
-        if (writes_U)
+            Slab fcs;
+            double *fc = nullptr;
+            if (with_fc) {
+                if (fc_dist) {
+                    const LevelGeom &gc = geom[li + 1];
+                    fcs = ranks[i].lv[li + 1].slab;
+                    fc = ranks[i].lv[li + 1].F;
+                    if (r > 0) pl.Fc_lo = fab.at<double>(r - 1, alloc[li + 1].F[r - 1]) - (ptrdiff_t)slab_of(gc, r - 1).row0 * M;
+                    if (r + 1 < comm.world) pl.Fc_hi = fab.at<double>(r + 1, alloc[li + 1].F[r + 1]) - (ptrdiff_t)slab_of(gc, r + 1).row0 * M;
+                    pl.fc_lo_end = cb[r] + HALO;
+                    pl.fc_hi_begin = cb[r + 1] - HALO;
+                } else {       // the rank's coarse rows land in its own full-size gather buffer; the broadcast follows the pass
+                    fcs.row0 = 0; fcs.rows = M; fcs.own_lo = cb[r]; fcs.own_hi = cb[r + 1];
+                    fc = fc_full[i];
+                }
+            }
+            slab_pass(g.N, L, S, in_mode, l.U, l.F, writes_U ? l.W : nullptr, l.slab, want_err, ranks[i].scal + scal_idx, M, fc,
+                      with_fc ? &fcs : nullptr, Nc, uc.empty() ? nullptr : uc[i], uc.empty() ? nullptr : &uc_slab[i], pl);
+        }
+        if (writes_U) {
             for (auto &st : ranks) std::swap(st.lv[li].U, st.lv[li].W);
+            std::swap(alloc[li].U, alloc[li].W);
+        }
+    }
+
+    // Agglomeration boundary: every rank sends its rows [cb[r], cb[r+1]) of the M x M restricted grid (already in its own
+    // gather buffer) to the same place in every other rank's gather buffer, then waits for everybody else's rows.
+    void gather_all(int M, const std::vector<int> &cb, unsigned int g)
+    {
+        Context &c = ctx();
+        for (size_t i = 0; i < ranks.size(); ++i) {        // all broadcasts are queued before any wait (one stream when emulated)
+            const int r = ranks[i].rank;
+            const size_t off = fab.gather_off(g) + (size_t)cb[r] * M * sizeof(double), count = (size_t)(cb[r + 1] - cb[r]) * M;
+            const double *dst_h[MAX_WORLD] = {};
+            unsigned int *flag_h[MAX_WORLD] = {};
+            int n = 0;
+            for (int q = 0; q < comm.world; ++q) {
+                if (q == r) continue;
+                dst_h[n] = fab.at<double>(q, off);
+                flag_h[n] = fab.peer[q].words + W_GATHER + r;
+                ++n;
+            }
+            Fabric::Tables &t = fab.tables[i];
+            const int par = (int)(g & 1u);
+            if (memcmp(t.dst_h[par], dst_h, sizeof dst_h) || memcmp(t.flag_h[par], flag_h, sizeof flag_h)) {   // same every cycle: uploaded once
+                memcpy(t.dst_h[par], dst_h, sizeof dst_h);
+                memcpy(t.flag_h[par], flag_h, sizeof flag_h);
+                check(cudaMemcpyAsync(t.dst[par], dst_h, sizeof dst_h, cudaMemcpyHostToDevice, c.stream), "H2D gather table");
+                check(cudaMemcpyAsync(t.flag[par], flag_h, sizeof flag_h, cudaMemcpyHostToDevice, c.stream), "H2D gather table");
+            }
+            const int blocks = (int)std::max<size_t>(1, std::min<size_t>(2 * c.sm_count, (count / 2 + 255) / 256));
+            k_peer_bcast<<<blocks, 256, 0, c.stream>>>(fab.at<double>(r, off), count, n, t.dst[par], t.flag[par], g, c.counters + 12);
+            c.launches++;
+            check(cudaGetLastError(), "k_peer_bcast");
+        }
+        for (size_t i = 0; i < ranks.size(); ++i) {
+            const int r = ranks[i].rank;
+            k_wait_gather<<<1, 32, 0, c.stream>>>(fab.peer[r].words, comm.world, r, g);
+            c.launches++;
+            check(cudaGetLastError(), "k_wait_gather");
+        }
     }
 };
 
@@ -720,65 +695,168 @@ struct SourceCache {
     bool from_host = false;
 };
 SourceCache g_src;
+std::unique_ptr<Fabric> g_fabric;   // of the NCCL communicator (persistent: the arenas and their IPC mappings survive between calls)
+
+void drop_source_cache()
+{
+    if (g_src.F && ctx().ready) pool_free(g_src.F);
+    g_src = SourceCache();
+}
 
 const char *kRestrictArt = "             *\n             |\n Restriction |\n             |\n             *\n";
 const char *kProlongArt = "             *\n             |\nProlongation |\n             |\n             *\n";
 
-int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec *recs, int max_recs, mgCycleResult *res,
-             double *U_host_full, double *U_host_own, int *own_lo_out, int *own_hi_out)
+struct Header {
+    double L = 0, min_x = 0, min_y = 0;
+    int con_step = 0, con_N = 0, N_max = 0, N_min = 0;
+    std::vector<int> ladder;
+    size_t first_node = 7;
+};
+
+bool parse_header(const std::vector<double> &tok, Header &h)
+{
+    if (tok.size() < 7) return false;
+    h.L = tok[0]; h.min_x = tok[1]; h.min_y = tok[2];
+    h.con_step = (int)tok[3]; h.con_N = (int)tok[4]; h.N_max = (int)tok[5]; h.N_min = (int)tok[6];
+    if (h.con_N == 1) for (int n = h.N_max; n >= h.N_min; n /= 2) h.ladder.push_back(n);
+    if (h.con_N == 2) for (int n = h.N_max; n >= h.N_min; --n) h.ladder.push_back(n);
+    return true;
+}
+
+// Walks the node stream with the geometry only: the arena every rank needs (max over ranks, in bytes, above the two
+// gather buffers) and the largest gathered grid.  Mirrors the stack moves of run_dist exactly; agglomerated sub-streams
+// are skipped with the parse-only mode of the single-GPU interpreter.  Returns 0, or the error code run_dist would hit.
+int plan_arena(const std::vector<double> &tok, const Header &h, int world, int threshold, size_t &arena_need, size_t &gather_need)
+{
+    std::vector<LevelGeom> geom;
+    std::vector<std::vector<size_t>> tops;       // per level: tops before its allocation
+    std::vector<size_t> top((size_t)world, 0), peak((size_t)world, 0);
+    gather_need = 0;
+    auto push = [&](const LevelGeom &g, bool has_own_F) {
+        tops.push_back(top);
+        geom.push_back(g);
+        if (g.dist)
+            for (int r = 0; r < world; ++r) {
+                top[r] += (has_own_F ? 3 : 2) * slab_bytes(g, r);
+                peak[r] = std::max(peak[r], top[r]);
+            }
+    };
+    auto pop = [&]() { top = tops.back(); tops.pop_back(); geom.pop_back(); };
+    push(top_geometry(h.N_max, world, threshold), false);
+    size_t cur = h.first_node, pos = 0;
+    int init = 1, n_recs = 0;
+    std::string why;
+    while (cur < tok.size()) {
+        if (!geom.back().dist && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
+            int c2 = (int)cur, p2 = (int)pos;
+            double *u = nullptr, *w = nullptr;
+            const int rc = mgRunSubcycle(tok.data(), (int)tok.size(), &c2, &p2, h.ladder.data(), (int)h.ladder.size(), h.con_step, h.con_N, h.L,
+                                         geom.back().N, &u, &w, nullptr, (int)geom.size() - 1, &init, MG_RUN_FUSED | MG_RUN_QUIET, nullptr, 0,
+                                         &n_recs, 0);
+            if (rc) return rc;
+            if ((size_t)c2 == cur) return 7;     // no progress: malformed stream
+            cur = (size_t)c2; pos = (size_t)p2;
+            continue;
+        }
+        const int node = (int)tok[cur++];
+        if (node == 2) break;
+        if (node == -1) {
+            int step, next_N;
+            if (h.con_step == 0) { if (cur >= tok.size()) return 3; step = (int)tok[cur++]; } else step = h.con_step;
+            if (h.con_N == 0) { if (cur >= tok.size()) return 3; next_N = (int)tok[cur++]; }
+            else { if (pos + 1 >= h.ladder.size()) return 4; next_N = h.ladder[++pos]; }
+            if (step == 0) continue;
+            LevelGeom coarse;
+            if (!induce_geometry(geom.back(), next_N, world, threshold, coarse, why)) return 20;
+            if (!coarse.dist) gather_need = std::max(gather_need, ((size_t)next_N * next_N * sizeof(double) + 255) / 256 * 256);
+            push(coarse, true);
+        } else if (node == 0) {
+            return 21;                           // an exact solve on a distributed level
+        } else if (node == 1) {
+            if (h.con_step == 0) { if (cur >= tok.size()) return 3; ++cur; }
+            if (h.con_N != 0 && pos > 0) --pos;
+            if (geom.size() < 2) return 5;
+            pop();
+            if (geom.size() == 1) init = 0;
+        } else return 6;
+    }
+    arena_need = 0;
+    for (int r = 0; r < world; ++r) arena_need = std::max(arena_need, peak[r]);
+    return 0;
+}
+
+struct RunIo {                 // where the top-level source comes from and where the solution goes
+    const double *F_host_full = nullptr;   // emulation: the whole N_max^2 source on the host (each rank uploads its slab)
+    const double *F_slab_dev = nullptr;    // one rank per process: its source slab, already on the device (rows [row0, row0+rows))
+    double *U_host_full = nullptr;         // emulation: assembled solution
+    double *U_host_own = nullptr;          // the rank's owned rows -> host (synchronous)
+    double *U_dev_own = nullptr;           // the rank's owned rows -> device buffer (stream-ordered copy; batch call)
+    int *own_lo = nullptr, *own_hi = nullptr;
+};
+
+int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags, mgTraceRec *recs, int max_recs, mgCycleResult *res,
+             const RunIo &io)
 {
     std::ifstream f(path);
     if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
     std::vector<double> tok;
     for (double d; f >> d;) tok.push_back(d);
-    if (tok.size() < 7) return 2;
-    size_t cur = 0;
+    Header h;
+    if (!parse_header(tok, h)) return 2;
+    const std::vector<int> &ladder = h.ladder;
+    const double L = h.L, min_x = h.min_x, min_y = h.min_y;
+    const int con_step = h.con_step, con_N = h.con_N, N_max = h.N_max;
+    size_t cur = h.first_node, pos = 0;
     auto have = [&](size_t n) { return cur + n <= tok.size(); };
     auto next_int = [&]() { return (int)tok[cur++]; };
-    double L, min_x, min_y;
-    int con_step, con_N, N_max, N_min;
-    L = tok[cur++]; min_x = tok[cur++]; min_y = tok[cur++];
-    con_step = next_int(); con_N = next_int(); N_max = next_int(); N_min = next_int();
-    std::vector<int> ladder;
-    if (con_N == 1) for (int n = N_max; n >= N_min; n /= 2) ladder.push_back(n);
-    if (con_N == 2) for (int n = N_max; n >= N_min; --n) ladder.push_back(n);
-    size_t pos = 0;
     const bool quiet = (flags & MG_RUN_QUIET) != 0 || !comm.is_local(0);
-
-    DistCycle cy(comm, threshold);
     Context &c = ctx();
+
+    // ---- arenas: sized from a dry walk of the node stream (every rank computes the same numbers), created or grown collectively
+    {
+        size_t arena_need = 0, gather_need = 0;
+        const int prc = plan_arena(tok, h, comm.world, threshold, arena_need, gather_need);
+        if (prc == 20) fail(-40, "a distributed level needs an even size and a fusable transfer pair: raise the threshold");
+        if (prc == 21) fail(-41, "the exact solver runs on an agglomerated level: lower the coarsest size or raise the threshold");
+        if (prc) return prc;
+        const size_t g_need = std::max(gather_need, fab.gather_bytes);
+        if (!fab.reserve(2 * g_need + arena_need, g_need)) return 30;
+    }
+
+    DistCycle cy(comm, fab, threshold);
     {
         const LevelGeom g = top_geometry(N_max, comm.world, threshold);
         // one-rank-per-process runs may keep the top-level source slab between calls
-        const bool cacheable = (flags & MG_RUN_SKIP_SOURCE) && cy.ranks.size() == 1;
-        double *borrowed = nullptr;
+        const bool cacheable = (flags & MG_RUN_SKIP_SOURCE) && cy.ranks.size() == 1 && !io.F_slab_dev && !io.F_host_full;
+        double *borrowed = const_cast<double *>(io.F_slab_dev);
         if (cacheable) {
             const Slab s0 = slab_of(g, cy.ranks[0].rank);
             const bool hit = g_src.F && g_src.N == N_max && g_src.world == comm.world && g_src.rank == cy.ranks[0].rank &&
                              g_src.row0 == s0.row0 && g_src.rows == s0.rows &&
                              (g_src.from_host || (g_src.L == L && g_src.min_x == min_x && g_src.min_y == min_y));
-            if (!hit && (g.dist || cy.ranks[0].rank == 0)) {
-                if (g_src.F) pool_free(g_src.F);
-                g_src = SourceCache();
+            if (!hit) {
+                drop_source_cache();
                 g_src.F = (double *)pool_alloc((size_t)s0.rows * N_max * sizeof(double));
                 g_src.N = N_max; g_src.world = comm.world; g_src.rank = cy.ranks[0].rank; g_src.row0 = s0.row0; g_src.rows = s0.rows;
                 g_src.L = L; g_src.min_x = min_x; g_src.min_y = min_y;
                 launch_source(N_max, L, g_src.F, min_x, min_y, false, s0.row0, s0.rows);
             }
-            if (g.dist || cy.ranks[0].rank == 0) borrowed = g_src.F;
+            borrowed = g_src.F;
         }
         cy.push(g, borrowed);
         if (!borrowed)
             for (auto &st : cy.ranks) {
                 RankLevel &l = st.lv[0];
-                if (l.present) launch_source(N_max, L, l.F, min_x, min_y, false, l.slab.row0, l.slab.rows);   // halo rows computed locally
+                if (io.F_host_full)      // emulation with a host source: every rank takes its rows, halo included
+                    check(cudaMemcpyAsync(l.F, io.F_host_full + (size_t)l.slab.row0 * N_max, (size_t)l.slab.rows * N_max * sizeof(double),
+                                          cudaMemcpyHostToDevice, c.stream), "H2D source slab");
+                else launch_source(N_max, L, l.F, min_x, min_y, false, l.slab.row0, l.slab.rows);   // halo rows computed locally
             }
     }
     check(cudaStreamSynchronize(c.stream), "sync");
 
     // Error sums of fixed-step nodes stay on the device as per-rank partials in consecutive scal slots;
-    // ONE all-reduce per batch (before an agglomerated sub-cycle, at the end, or when the slots run
-    // out) turns them into the trace records -- one collective instead of one per node.
+    // ONE all-reduce per batch (at the end, or when the slots run out) turns them into the trace records.
     int n_recs = 0;
     auto record = [&](int node, int N, int steps, double err) {
         const int r = n_recs++;
@@ -791,8 +869,8 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
         if (cy.scal_used_ > 0) {
             double sums[SCAL_BATCH];
             cy.allreduce(0, cy.scal_used_);
-            check(cudaMemcpyAsync(sums, cy.ranks[0].scal, cy.scal_used_ * sizeof(double), cudaMemcpyDeviceToHost, cy.ts.cs), "D2H sums");
-            cy.ts.sync();
+            check(cudaMemcpyAsync(sums, cy.ranks[0].scal, cy.scal_used_ * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H sums");
+            check(cudaStreamSynchronize(c.stream), "sync");
             for (const auto &d : deferred) {
                 if (!recs || d.first >= max_recs) continue;
                 const double v = sums[d.second], N = recs[d.first].N;
@@ -801,8 +879,8 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             deferred.clear();
             cy.scal_used_ = 0;
         }
-        cy.ts.sync();
-        mgSubcycleHarvest();                     // scalars of the agglomerated sub-cycles (rank 0)
+        check(cudaStreamSynchronize(c.stream), "sync");
+        mgSubcycleHarvest();                     // scalars of the agglomerated sub-cycles
     };
     auto next_scal = [&]() {
         if (cy.scal_used_ == SCAL_BATCH) harvest();
@@ -812,13 +890,29 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     auto reduced_now = [&](int idx) {
         cy.allreduce(idx);
         double s = 0.0;
-        check(cudaMemcpyAsync(&s, cy.ranks[0].scal + idx, sizeof(double), cudaMemcpyDeviceToHost, cy.ts.cs), "D2H");
-        check(cudaStreamSynchronize(cy.ts.cs), "sync");
+        check(cudaMemcpyAsync(&s, cy.ranks[0].scal + idx, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+        check(cudaStreamSynchronize(c.stream), "sync");
         return s;
     };
-    const std::vector<double *> no_fc;
+    // the error-trigger loop on a distributed level (:216-230 / :388-402): one sweep per pass, the all-reduced error decides
+    auto trigger_loop = [&](int li, bool first_from_zero, int N, int &done, double &err_host) {
+        double slope = TRIGGER + 1.0, prev = 0.0;
+        done = 0;
+        while (slope > TRIGGER) {
+            const int idx = next_scal();
+            cy.pass(li, L, 1, (done == 0 && first_from_zero) ? 1 : 0, true, idx, 0, false, false, {}, {}, 0, {}, {});
+            const double s = reduced_now(idx);
+            err_host = (s + s) / N / N;
+            ++done;
+            if (done > 1) slope = std::fabs(err_host - prev);
+            prev = err_host;
+            if (c.err_code) break;
+        }
+    };
     const std::vector<const double *> no_uc;
     const std::vector<Slab> no_slab;
+    const std::vector<double *> no_fc;
+    const std::vector<int> no_cb;
 
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
@@ -827,7 +921,7 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     const auto wall0 = std::chrono::steady_clock::now();
     cudaEventRecord(ev0, c.stream);
 
-    // MG_DIST_TRACE=1: per-node time line (device time on the compute stream, host enqueue time)
+    // MG_DIST_TRACE=1: per-node time line (device time on the stream, host enqueue time)
     struct Mark { const char *what; int N; cudaEvent_t ev; std::chrono::steady_clock::time_point host; };
     std::vector<Mark> marks;
     const bool tracing = getenv("MG_DIST_TRACE") && atoi(getenv("MG_DIST_TRACE")) != 0;
@@ -843,19 +937,19 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     int rc = 0, node = 0;
     std::string why;
     while (have(1)) {
-        // ---- agglomerated sub-cycle: everything that happens at or below a level held by rank 0
-        // alone is run by the single-GPU interpreter (fused nodes + coarse tail kernel) on rank 0;
-        // the other ranks parse the same nodes without executing them.
+        // ---- agglomerated sub-cycle: everything that happens at or below a level every rank holds in full is run by the
+        // single-GPU interpreter (fused nodes + coarse tail kernel), redundantly on every rank.
         if (!cy.geom.back().dist && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
             const int li = (int)cy.geom.size() - 1;
             int icur = (int)cur, ipos = (int)pos, n_rec_io = n_recs, init_io = cy.init_;
             int sub_rc = 0;
-            for (auto &st : cy.ranks) {
-                RankLevel &l = st.lv[li];
+            for (size_t i = 0; i < cy.ranks.size(); ++i) {
+                RankLevel &l = cy.ranks[i].lv[li];
                 int c2 = (int)cur, p2 = (int)pos, r2 = n_recs, i2 = cy.init_;
+                const bool lead = i == 0;    // emulation: only the first local rank reports into the caller's records
                 sub_rc = mgRunSubcycle(tok.data(), (int)tok.size(), &c2, &p2, ladder.data(), (int)ladder.size(), con_step, con_N, L,
-                                       cy.geom[li].N, &l.U, &l.W, l.F, li, &i2, flags | MG_RUN_DEFER_HARVEST,
-                                       (st.rank == 0 || !comm.is_local(0)) ? recs : nullptr, max_recs, &r2, st.rank == 0 ? 1 : 0);
+                                       cy.geom[li].N, &l.U, &l.W, l.F, li, &i2, lead ? (flags | MG_RUN_DEFER_HARVEST) : flags,
+                                       lead ? recs : nullptr, lead ? max_recs : 0, &r2, 1);
                 icur = c2; ipos = p2; n_rec_io = r2; init_io = i2;
                 if (sub_rc) break;
             }
@@ -879,65 +973,39 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             const bool zero_init = !cy.restart_top();
             LevelGeom coarse;
             if (!cy.induce(fine, next_N, coarse, why)) { fail(-40, why); rc = 20; break; }
-            cy.push(coarse);
+            const unsigned int gather_no = coarse.dist ? 0u : ++fab.gathers;
+            cy.push(coarse, nullptr, !coarse.dist, gather_no);
 
-            // F_c target per rank: the coarse slab's F if the coarse level is distributed, else a
-            // temporary holding exactly the rank's coarse rows (rank 0 writes into the full array)
             const std::vector<int> cb = coarse_bounds(fine, next_N, comm.world);
-            std::vector<double *> fc_tmp(cy.ranks.size(), nullptr), fc(cy.ranks.size(), nullptr);
-            std::vector<Slab> fc_slab(cy.ranks.size());
-            for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                RankState &st = cy.ranks[i];
-                fc[i] = st.lv[li + 1].F;
-                fc_slab[i] = st.lv[li + 1].slab;
-                if (coarse.dist || st.rank == 0) continue;
-                fc_slab[i].row0 = fc_slab[i].own_lo = cb[st.rank];
-                fc_slab[i].own_hi = cb[st.rank + 1];
-                fc_slab[i].rows = cb[st.rank + 1] - cb[st.rank];
-                fc[i] = fc_tmp[i] = (double *)pool_alloc((size_t)std::max(1, fc_slab[i].rows) * next_N * sizeof(double));
-            }
-
-            if (step > 0) {
-                // passes of at most 3 sweeps; the last one also restricts
-                const int n_pass = (step + 2) / 3, idx = next_scal();
+            std::vector<double *> fc_full;
+            if (!coarse.dist)
+                for (auto &st : cy.ranks) fc_full.push_back(st.lv[li + 1].F);
+            int done = step;
+            double err_host = 0.0;
+            bool host_err = false;
+            if (step == -1) {           // :194-240: trigger loop, then the residual + restriction of the result
+                trigger_loop(li, zero_init, fine.N, done, err_host);
+                host_err = true;
+                cy.pass(li, L, 0, 0, false, 0, next_N, true, coarse.dist, cb, fc_full, 0, no_uc, no_slab);
+            } else {
+                // step > 0: passes of at most 3 sweeps, the last one also restricts.  step < -1 (:244-259): doSmoothing with a
+                // negative count = no sweep; the grid is still zeroed, the error evaluated, the residual restricted.
+                const int sweeps = step > 0 ? step : 0;
+                const int n_pass = std::max(1, (sweeps + 2) / 3), idx = next_scal();
+                if (sweeps == 0 && zero_init)
+                    for (auto &st : cy.ranks)
+                        check(cudaMemsetAsync(st.lv[li].U, 0, (size_t)st.lv[li].slab.rows * fine.N * sizeof(double), c.stream), "memset");
                 for (int k = 0; k < n_pass; ++k) {
-                    const int S = step / n_pass + (k < step % n_pass ? 1 : 0);
+                    const int S = sweeps / n_pass + (k < sweeps % n_pass ? 1 : 0);
                     const bool first = k == 0, last = k + 1 == n_pass;
-                    if (last) cy.pass(li, L, S, (first && zero_init) ? 1 : 0, true, idx, next_N, fc, fc_slab, coarse.dist, 0, no_uc, no_slab);
-                    else      cy.pass(li, L, S, (first && zero_init) ? 1 : 0, false, idx, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
+                    const int in_mode = (first && zero_init && sweeps > 0) ? 1 : 0;
+                    if (last) cy.pass(li, L, S, in_mode, true, idx, next_N, true, coarse.dist, cb, fc_full, 0, no_uc, no_slab);
+                    else      cy.pass(li, L, S, in_mode, false, idx, 0, false, false, no_cb, no_fc, 0, no_uc, no_slab);
                 }
-                deferred.push_back({record(-1, fine.N, step, 0.0), idx});
-            } else {   // trigger loop: the scalar is needed after every sweep
-                double slope = TRIGGER + 1.0, prev = 0.0, err_host = 0.0;
-                int done = 0;
-                while (slope > TRIGGER) {
-                    const int idx = next_scal();
-                    cy.pass(li, L, 1, (done == 0 && zero_init) ? 1 : 0, true, idx, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
-                    const double s = reduced_now(idx);
-                    err_host = (s + s) / fine.N / fine.N;
-                    ++done;
-                    if (done > 1) slope = std::fabs(err_host - prev);
-                    prev = err_host;
-                    if (c.err_code) break;
-                }
-                cy.pass(li, L, 0, 0, false, 0, next_N, fc, fc_slab, coarse.dist, 0, no_uc, no_slab);   // residual + restriction only
-                record(-1, fine.N, done, err_host);
+                deferred.push_back({record(-1, fine.N, done, 0.0), idx});
             }
-            if (!coarse.dist) {           // gather the slabs' coarse rows into rank 0's full grid
-                std::vector<Xfer> xs;
-                for (int k = 1; k < comm.world; ++k) {
-                    const double *src = nullptr;
-                    double *dst = nullptr;
-                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                        if (cy.ranks[i].rank == k) src = fc_tmp[i];
-                        if (cy.ranks[i].rank == 0) dst = cy.ranks[i].lv[li + 1].F + (size_t)cb[k] * next_N;
-                    }
-                    if (!comm.is_local(k) && !comm.is_local(0)) continue;
-                    xs.push_back({k, 0, src, dst, (size_t)(cb[k + 1] - cb[k]) * next_N});
-                }
-                cy.transfer_now(xs);
-            }
-            for (double *p : fc_tmp) pool_free(p);
+            if (host_err) record(-1, fine.N, done, err_host);
+            if (!coarse.dist) cy.gather_all(next_N, cb, gather_no);
             if (!quiet) fputs(kRestrictArt, stdout);
             mark(coarse.dist ? "down" : "down+gather", fine.N);
         } else if (node == 0) {
@@ -955,73 +1023,46 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             const LevelGeom coarse = cy.geom[lc], fine = cy.geom[lf];
             if (!fine.dist) { rc = 7; break; }   // cannot happen: levels below an agglomerated one belong to the sub-cycle
 
-            // ---- U_c rows with halo on every rank (halos of distributed arrays are current by construction)
-            std::vector<double *> uc_tmp(cy.ranks.size(), nullptr);
+            // U_c: the rank's coarse slab (halos current by construction) or its own full copy of the agglomerated level
             std::vector<const double *> uc(cy.ranks.size(), nullptr);
             std::vector<Slab> uc_slab(cy.ranks.size());
             for (size_t i = 0; i < cy.ranks.size(); ++i) { uc[i] = cy.ranks[i].lv[lc].U; uc_slab[i] = cy.ranks[i].lv[lc].slab; }
-            if (!coarse.dist) {          // scatter rank 0's full coarse grid: each rank gets its rows plus halo
-                const std::vector<int> cb = coarse_bounds(fine, coarse.N, comm.world);
-                std::vector<Xfer> xs;
-                const double *full = nullptr;
-                for (auto &st : cy.ranks) if (st.rank == 0) full = st.lv[lc].U;
-                for (int k = 1; k < comm.world; ++k) {
-                    Slab s;
-                    s.own_lo = cb[k]; s.own_hi = cb[k + 1];
-                    s.row0 = std::max(0, cb[k] - HALO);
-                    s.rows = std::min(coarse.N, cb[k + 1] + HALO) - s.row0;
-                    double *dst = nullptr;
-                    for (size_t i = 0; i < cy.ranks.size(); ++i) {
-                        if (cy.ranks[i].rank != k) continue;
-                        uc_slab[i] = s;
-                        uc[i] = dst = uc_tmp[i] = (double *)pool_alloc((size_t)s.rows * coarse.N * sizeof(double));
-                    }
-                    if (!comm.is_local(k) && !comm.is_local(0)) continue;
-                    xs.push_back({0, k, full ? full + (size_t)s.row0 * coarse.N : nullptr, dst, (size_t)s.rows * coarse.N});
-                }
-                cy.transfer_now(xs);
-            }
 
             const int fixed = step > 0 ? step : 0;
             const int n_pass = std::max(1, (fixed + 2) / 3), idx = next_scal();
             for (int k = 0; k < n_pass; ++k) {
                 const int S = fixed / n_pass + (k < fixed % n_pass ? 1 : 0);
                 const bool first = k == 0, last = k + 1 == n_pass;
-                if (first) cy.pass(lf, L, S, 2, last && step > 0, idx, 0, no_fc, no_slab, false, coarse.N, uc, uc_slab);
-                else       cy.pass(lf, L, S, 0, last && step > 0, idx, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
+                if (first) cy.pass(lf, L, S, 2, last && step > 0, idx, 0, false, false, no_cb, no_fc, coarse.N, uc, uc_slab);
+                else       cy.pass(lf, L, S, 0, last && step > 0, idx, 0, false, false, no_cb, no_fc, 0, no_uc, no_slab);
             }
             if (step > 0) {
                 deferred.push_back({record(1, fine.N, step, 0.0), idx});
-            } else if (step < 0) {
-                double slope = TRIGGER + 1.0, prev = 0.0, err_host = 0.0;
+            } else if (step == -1) {
                 int done = 0;
-                while (slope > TRIGGER) {
-                    const int j = next_scal();
-                    cy.pass(lf, L, 1, 0, true, j, 0, no_fc, no_slab, false, 0, no_uc, no_slab);
-                    const double s = reduced_now(j);
-                    err_host = (s + s) / fine.N / fine.N;
-                    ++done;
-                    if (done > 1) slope = std::fabs(err_host - prev);
-                    prev = err_host;
-                    if (c.err_code) break;
-                }
+                double err_host = 0.0;
+                trigger_loop(lf, false, fine.N, done, err_host);
                 record(1, fine.N, done, err_host);
+            } else if (step < -1) {              // :410-421: no sweep, the error is still evaluated
+                const int j = next_scal();
+                cy.pass(lf, L, 0, 0, true, j, 0, false, false, no_cb, no_fc, 0, no_uc, no_slab);
+                deferred.push_back({record(1, fine.N, step, 0.0), j});
             } else record(1, fine.N, 0, 0.0);
-            for (double *p : uc_tmp) pool_free(p);
             if (!quiet) fputs(kProlongArt, stdout);
             cy.pop();
-            mark(coarse.dist ? "up" : "scatter+up", fine.N);
+            mark(coarse.dist ? "up" : "up (from the sub-cycle)", fine.N);
         } else { rc = 6; break; }
     }
-    cy.ts.to_compute();                          // the timed span ends when both streams have drained
     cudaEventRecord(ev1, c.stream);
+    if (c.err_code && rc == 0) rc = 10;
+    if (rc) fab.abort_peers(c.stream);           // the other ranks must not wait for passes that will never come
     harvest();
     const auto wall1 = std::chrono::steady_clock::now();
     for (size_t i = 1; i < marks.size(); ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, marks[i - 1].ev, marks[i].ev);
         if (comm.is_local(0))
-            fprintf(stderr, "[mg trace] %-12s N=%-6d device %8.3f ms   host enqueue %8.3f ms\n", marks[i].what, marks[i].N, ms,
+            fprintf(stderr, "[mg trace] %-24s N=%-6d device %8.3f ms   host enqueue %8.3f ms\n", marks[i].what, marks[i].N, ms,
                     std::chrono::duration<double, std::milli>(marks[i].host - marks[i - 1].host).count());
     }
     for (Mark &m : marks) cudaEventDestroy(m.ev);
@@ -1047,23 +1088,23 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
             for (auto &st : cy.ranks) {
                 RankLevel &l = st.lv[0];
                 check(cudaMemsetAsync(st.scal + 60, 0, sizeof(double), c.stream), "memset");
-                if (!l.present) continue;
+                if (!g.dist && st.rank != 0) continue;     // every rank holds the whole grid: count it once
                 launch_source(g.N, L, l.W, min_x, min_y, true, l.slab.row0, l.slab.rows);
                 const size_t off = (size_t)(l.slab.own_lo - l.slab.row0) * g.N, cnt = (size_t)(l.slab.own_hi - l.slab.own_lo) * g.N;
                 launch_mean_abs_diff(cnt, l.W + off, l.U + off, 1.0, st.scal + 60);
             }
-            const double s = reduced_now(60);   // ranks without a share contribute 0
+            const double s = reduced_now(60);
             res->mg_error = s / ((double)g.N * (double)g.N);
         }
         // ---- solution out
         for (auto &st : cy.ranks) {
             RankLevel &l = st.lv[0];
-            if (!l.present) continue;
             const size_t off = (size_t)(l.slab.own_lo - l.slab.row0) * g.N, cnt = (size_t)(l.slab.own_hi - l.slab.own_lo) * g.N;
-            if (U_host_full) check(cudaMemcpyAsync(U_host_full + (size_t)l.slab.own_lo * g.N, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
-            if (U_host_own) check(cudaMemcpyAsync(U_host_own, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
-            if (own_lo_out) *own_lo_out = l.slab.own_lo;
-            if (own_hi_out) *own_hi_out = l.slab.own_hi;
+            if (io.U_host_full) check(cudaMemcpyAsync(io.U_host_full + (size_t)l.slab.own_lo * g.N, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
+            if (io.U_host_own) check(cudaMemcpyAsync(io.U_host_own, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H U");
+            if (io.U_dev_own) check(cudaMemcpyAsync(io.U_dev_own, l.U + off, cnt * sizeof(double), cudaMemcpyDeviceToDevice, c.stream), "D2D U");
+            if (io.own_lo) *io.own_lo = l.slab.own_lo;
+            if (io.own_hi) *io.own_hi = l.slab.own_hi;
         }
         check(cudaStreamSynchronize(c.stream), "sync");
         if (!quiet && res) {
@@ -1073,20 +1114,39 @@ int run_dist(Comm &comm, const char *path, int threshold, int flags, mgTraceRec 
     return rc;
 }
 
+Fabric *nccl_fabric()
+{
+    if (!g_nccl_comm) return nullptr;
+    if (!g_fabric) g_fabric.reset(new Fabric(*g_nccl_comm));
+    return g_fabric.get();
+}
+
 }  // namespace
+
+void dist_release_on_shutdown()
+{
+    g_fabric.reset();
+    g_src = SourceCache();                      // the pool that held the slab is being destroyed by the caller
+}
+
 }  // namespace mg
 
 using namespace mg;
 
 extern "C" {
 
-int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags, double *U_host, mgTraceRec *recs,
+int mgDistEmuRunCycleFile(const char *path, int world, int threshold, int flags, const double *F_host, double *U_host, mgTraceRec *recs,
                           int max_recs, mgCycleResult *res)
 {
     if (!ensure_ready()) return 10;
-    if (world < 1) return 11;
+    if (world < 1 || world > MAX_WORLD) return 11;
     EmuComm comm(world);
-    return run_dist(comm, path, threshold, flags, recs, max_recs, res, U_host, nullptr, nullptr, nullptr);
+    Fabric fab(comm);
+    if (!fab.ok) return 30;
+    RunIo io;
+    io.F_host_full = F_host;
+    io.U_host_full = U_host;
+    return run_dist(comm, fab, path, threshold, flags, recs, max_recs, res, io);
 }
 
 int mgDistPlan(const int *ladder, int n_levels, int world, int threshold, int *out, int max_out)
@@ -1125,6 +1185,7 @@ int mgDistInit(int rank, int world, const void *id128)
     if (!ensure_ready()) return 10;
     if (!g_nccl.load()) return 1;
     if (g_nccl_comm) return 0;
+    if (world > MAX_WORLD) { fail(-35, "mgDistInit: at most 16 ranks"); return 3; }
     std::unique_ptr<NcclComm> cm(new NcclComm());
     cm->world = world;
     cm->rank = rank;
@@ -1132,9 +1193,9 @@ int mgDistInit(int rank, int world, const void *id128)
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     if (!cm->ok(g_nccl.CommInitRank(&cm->comm, world, id, rank), "ncclCommInitRank")) return 2;
+    if (!cm->reserve((size_t)(MAX_WORLD + 1) * 256)) { fail(-38, "mgDistInit: cudaMalloc"); return 4; }
     g_nccl_comm = std::move(cm);
-    if (world > 1 && staged_requested()) g_nccl_comm->setup_staged();   // collective; falls back to NCCL transfers if any rank fails
-    return 0;
+    return nccl_fabric()->ok ? 0 : 30;          // flag words allocated and mapped on every rank (collective)
 }
 
 int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, int *own_hi)
@@ -1142,8 +1203,7 @@ int mgDistSourceSlab(int N, int threshold, int *row0, int *rows, int *own_lo, in
     if (!g_nccl_comm) { fail(-34, "mgDistSourceSlab: call mgDistInit first"); return 12; }
     const LevelGeom g = top_geometry(N, g_nccl_comm->world, threshold);
     const Slab s = slab_of(g, g_nccl_comm->rank);
-    const bool present = g.dist || g_nccl_comm->rank == 0;
-    *row0 = s.row0; *rows = present ? s.rows : 0; *own_lo = s.own_lo; *own_hi = present ? s.own_hi : s.own_lo;
+    *row0 = s.row0; *rows = s.rows; *own_lo = s.own_lo; *own_hi = s.own_hi;
     return 0;
 }
 
@@ -1156,8 +1216,7 @@ int mgDistUploadSource(int N, int threshold, const double *F_slab_host)
     const bool match = g_src.F && g_src.N == N && g_src.world == g_nccl_comm->world && g_src.rank == g_nccl_comm->rank &&
                        g_src.row0 == row0 && g_src.rows == rows;
     if (!match) {
-        if (g_src.F) pool_free(g_src.F);
-        g_src = SourceCache();
+        drop_source_cache();
         g_src.F = (double *)pool_alloc((size_t)rows * N * sizeof(double));
         g_src.N = N; g_src.world = g_nccl_comm->world; g_src.rank = g_nccl_comm->rank; g_src.row0 = row0; g_src.rows = rows;
     }
@@ -1174,8 +1233,8 @@ int mgDistDownloadSource(int N, double *F_slab_host)
     return 0;
 }
 
-// doSmoothing on row slabs, repeated: `reps` times `step` Jacobi sweeps (passes of <= 3 fused sweeps,
-// one halo exchange per pass, error all-reduced once per repetition) on the analytic source grid,
+// doSmoothing on row slabs, repeated: `reps` times `step` Jacobi sweeps (passes of <= 3 fused sweeps, halo rows stored
+// into the neighbours' slabs by every pass, error all-reduced once per repetition) on the analytic source grid,
 // starting from U = 0.  BASELINE config 5's smoothing-only stress; N up to 65536 (64-bit indexing).
 // Works without mgDistInit on one GPU.  U_own_host (optional) receives the rank's owned rows.
 int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, double *error_out, double *U_own_host, int *own_lo,
@@ -1184,54 +1243,72 @@ int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, 
     if (!ensure_ready()) return 10;
     if (N % 2 || N < 64 || step < 1 || reps < 1) return 1;
     EmuComm solo(1);
+    std::unique_ptr<Fabric> solo_fab;
     Comm &comm = g_nccl_comm ? static_cast<Comm &>(*g_nccl_comm) : static_cast<Comm &>(solo);
+    if (!g_nccl_comm) solo_fab.reset(new Fabric(solo));
+    Fabric &fab = g_nccl_comm ? *nccl_fabric() : *solo_fab;
     const int rank = g_nccl_comm ? g_nccl_comm->rank : 0;
     Context &c = ctx();
     const LevelGeom g = top_geometry(N, comm.world, 0);
     if (comm.world > 1 && !g.dist) return 2;
+    // arena: U and W slabs of every rank (F is local); a local allocation failure travels through the collective reserve
+    size_t need = 0;
+    for (int r = 0; r < comm.world; ++r) need = std::max(need, 2 * slab_bytes(g, r));
+    if (!fab.reserve(2 * fab.gather_bytes + need, fab.gather_bytes)) return 3;
+    std::fill(fab.top.begin(), fab.top.end(), 2 * fab.gather_bytes);
+    std::vector<size_t> bytes((size_t)comm.world);
+    for (int r = 0; r < comm.world; ++r) bytes[r] = slab_bytes(g, r);
+    std::vector<size_t> offU = fab.alloc(bytes), offW = fab.alloc(bytes);
     const Slab sl = slab_of(g, rank);
-    const size_t bytes = (size_t)sl.rows * N * sizeof(double);
-    double *U = (double *)pool_alloc(bytes), *W = (double *)pool_alloc(bytes), *F = (double *)pool_alloc(bytes);
-    double *scal = (double *)pool_alloc(64 * sizeof(double));
-    if (!U || !W || !F || !scal) return 3;
+    const size_t sbytes = (size_t)sl.rows * N * sizeof(double);
+    double *U = fab.at<double>(rank, offU[rank]), *W = fab.at<double>(rank, offW[rank]);
+    double *F = (double *)pool_alloc(sbytes), *scal = (double *)pool_alloc(64 * sizeof(double));
+    const int mem_ok = comm.allreduce_min_host(F && scal ? 1 : 0);
+    if (!mem_ok) { pool_free(F); pool_free(scal); return 3; }
     launch_source(N, L, F, 0.0, 0.0, false, sl.row0, sl.rows);
-    check(cudaMemsetAsync(U, 0, bytes, c.stream), "memset");
-    check(cudaMemsetAsync(W, 0, bytes, c.stream), "memset");
+    check(cudaMemsetAsync(U, 0, sbytes, c.stream), "memset");
+    check(cudaMemsetAsync(W, 0, sbytes, c.stream), "memset");
+    if (comm.world > 1) { check(cudaStreamSynchronize(c.stream), "sync"); comm.allreduce_min_host(1); }   // every rank's arrays are zeroed before any peer store
 
-    TwoStream ts;
     const int n_pass = (step + 2) / 3;
     int rot = 0;
     auto one_rep = [&]() {
-        if (++rot == 48) { ts.sync(); rot = 1; }          // scal slots still queued for an all-reduce
+        if (++rot == 48) { check(cudaStreamSynchronize(c.stream), "sync"); rot = 1; }   // scal slots still queued for an all-reduce
         for (int k = 0; k < n_pass; ++k) {
             const int S = step / n_pass + (k < step % n_pass ? 1 : 0);
             const bool last = k + 1 == n_pass;
-            std::vector<Xfer> xs;
-            halo_xfers(g, comm, [&](int r) -> double * { return r == rank ? W : nullptr; }, xs);
-            ts.wait_halo();
-            if (ts.cs != ts.ms && !xs.empty()) {
-                slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, 1);
-                ts.edge_done();
-                comm.transfer(xs, ts.cs);
-                ts.halo_posted();
-                slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, 2);
-            } else {
-                slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, 0);
-                if (!xs.empty()) { comm.transfer(xs, ts.cs); ts.halo_posted(); }
+            const unsigned int prev = fab.seq, mine = ++fab.seq;
+            PeerLinks pl;
+            if (rank > 0) fab.wait32(c.stream, fab.peer[rank].words + W_FROM_LO, prev);
+            if (rank + 1 < comm.world) fab.wait32(c.stream, fab.peer[rank].words + W_FROM_HI, prev);
+            pl.flag_val = mine;
+            if (rank > 0) {
+                pl.flag_lo = fab.peer[rank - 1].words + W_FROM_HI;
+                pl.U_lo = fab.at<double>(rank - 1, offW[rank - 1]) - (ptrdiff_t)slab_of(g, rank - 1).row0 * N;
             }
+            if (rank + 1 < comm.world) {
+                pl.flag_hi = fab.peer[rank + 1].words + W_FROM_LO;
+                pl.U_hi = fab.at<double>(rank + 1, offW[rank + 1]) - (ptrdiff_t)slab_of(g, rank + 1).row0 * N;
+            }
+            pl.u_lo_end = sl.own_lo + HALO;
+            pl.u_hi_begin = sl.own_hi - HALO;
+            slab_pass(N, L, S, 0, U, F, W, sl, last, scal + rot, 0, nullptr, nullptr, 0, nullptr, nullptr, pl);
             std::swap(U, W);
+            std::swap(offU, offW);
         }
-        if (comm.world > 1) { ts.to_comm(); comm.allreduce_sum({scal + rot}, 1, ts.cs); }
+        if (comm.world > 1) comm.allreduce_sum({scal + rot}, 1, c.stream);
     };
     one_rep();                                   // warm-up (also NCCL connection set-up)
-    ts.to_compute();                             // the warm-up's last halo exchange lands before the reset
-    check(cudaMemsetAsync(U, 0, bytes, c.stream), "memset");
+    check(cudaStreamSynchronize(c.stream), "sync");
+    if (comm.world > 1) comm.allreduce_min_host(1);   // the warm-up's last halo rows have landed everywhere before the reset
+    check(cudaMemsetAsync(U, 0, sbytes, c.stream), "memset");
+    check(cudaStreamSynchronize(c.stream), "sync");
+    if (comm.world > 1) comm.allreduce_min_host(1);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, c.stream);
     for (int r = 0; r < reps; ++r) one_rep();
-    ts.to_compute();
     cudaEventRecord(e1, c.stream);
     double s = 0.0;
     check(cudaMemcpyAsync(&s, scal + rot, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
@@ -1249,16 +1326,19 @@ int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, 
     }
     if (own_lo) *own_lo = sl.own_lo;
     if (own_hi) *own_hi = sl.own_hi;
-    pool_free(U); pool_free(W); pool_free(F); pool_free(scal);
+    if (comm.world > 1) comm.allreduce_min_host(1);   // nobody frees while a neighbour may still store into its halos
+    pool_free(F); pool_free(scal);
     return c.err_code ? 10 : 0;
 }
 
 void mgDistShutdown(void)
 {
-    if (g_nccl_comm) {
+    if (ctx().ready) {
         cudaStreamSynchronize(ctx().stream);
-        cudaStreamSynchronize(ctx().comm_stream);
-        g_nccl_comm->staged.reset();
+        drop_source_cache();
+    }
+    g_fabric.reset();
+    if (g_nccl_comm) {
         g_nccl.CommDestroy(g_nccl_comm->comm);
         g_nccl_comm.reset();
     }
@@ -1269,7 +1349,70 @@ int mgDistRunCycleFile(const char *path, int threshold, int flags, double *U_own
 {
     if (!ensure_ready()) return 10;
     if (!g_nccl_comm) { fail(-34, "mgDistRunCycleFile: call mgDistInit first"); return 12; }
-    return run_dist(*g_nccl_comm, path, threshold, flags, recs, max_recs, res, nullptr, U_own_host, own_lo, own_hi);
+    RunIo io;
+    io.U_host_own = U_own_host;
+    io.own_lo = own_lo;
+    io.own_hi = own_hi;
+    return run_dist(*g_nccl_comm, *nccl_fabric(), path, threshold, flags, recs, max_recs, res, io);
+}
+
+// n independent problems through the same cycle file on the slabs of mgDistInit, HOST buffers per rank: F_slab_hosts[i] =
+// this rank's source rows [row0, row0+rows) of problem i (mgDistSourceSlab), U_own_hosts[i] receives its owned rows.
+// Double-buffered like mgRunCycleFileHostBatch: the upload of problem i+1 and the download of problem i-1 run on two copy
+// streams while the cycle of problem i computes.  Collective; bit-identical to n (mgDistUploadSource, mgDistRunCycleFile) pairs.
+int mgDistRunCycleFileHostBatch(const char *path, int threshold, int flags, int n, const double *const *F_slab_hosts,
+                                double *const *U_own_hosts, mgCycleResult *res)
+{
+    if (!ensure_ready()) return 10;
+    if (!g_nccl_comm) { fail(-34, "mgDistRunCycleFileHostBatch: call mgDistInit first"); return 12; }
+    if (n < 1 || !F_slab_hosts || !U_own_hosts) return 11;
+    std::ifstream f(path);
+    if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
+    double L, mx, my; int cs, cn, N_max, N_min;
+    f >> L >> mx >> my >> cs >> cn >> N_max >> N_min;
+    if (!f) return 2;
+    f.close();
+    int row0, rows, lo, hi;
+    if (mgDistSourceSlab(N_max, threshold, &row0, &rows, &lo, &hi)) return 12;
+    const size_t f_bytes = (size_t)rows * N_max * sizeof(double), u_bytes = (size_t)(hi - lo) * N_max * sizeof(double);
+    cudaStream_t compute = ctx().stream, up = nullptr, down = nullptr;
+    cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
+    double *dF[2] = {(double *)pool_alloc(f_bytes), n > 1 ? (double *)pool_alloc(f_bytes) : nullptr};
+    double *dU[2] = {(double *)pool_alloc(u_bytes), n > 1 ? (double *)pool_alloc(u_bytes) : nullptr};
+    std::vector<cudaEvent_t> uploaded((size_t)n), downloaded((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&downloaded[i], cudaEventDisableTiming);
+    }
+    // a local allocation failure must not leave the other ranks alone in the collective cycles: agree first
+    int rc = g_nccl_comm->allreduce_min_host((dF[0] && dU[0] && (n == 1 || (dF[1] && dU[1]))) ? 1 : 0) ? 0 : 12;
+    auto upload = [&](int i) {      // the previous reader of dF[i % 2], cycle i-2, has been waited for on the host
+        cudaMemcpyAsync(dF[i % 2], F_slab_hosts[i], f_bytes, cudaMemcpyHostToDevice, up);
+        cudaEventRecord(uploaded[i], up);
+    };
+    cudaStreamSynchronize(compute);
+    if (rc == 0) upload(0);
+    for (int i = 0; i < n && rc == 0; ++i) {
+        if (i + 1 < n) upload(i + 1);
+        cudaStreamWaitEvent(compute, uploaded[i], 0);
+        if (i >= 2) cudaStreamWaitEvent(compute, downloaded[i - 2], 0);      // dU[i % 2] is free again
+        RunIo io;
+        io.F_slab_dev = dF[i % 2];
+        io.U_dev_own = dU[i % 2];
+        rc = run_dist(*g_nccl_comm, *nccl_fabric(), path, threshold, flags | MG_RUN_SKIP_SOURCE, nullptr, 0, res ? res + i : nullptr, io);   // returns synchronised
+        if (rc) break;
+        cudaMemcpyAsync(U_own_hosts[i], dU[i % 2], u_bytes, cudaMemcpyDeviceToHost, down);
+        cudaEventRecord(downloaded[i], down);
+    }
+    cudaStreamSynchronize(up);
+    cudaStreamSynchronize(down);
+    if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = 13;
+    for (int i = 0; i < n; ++i) { cudaEventDestroy(uploaded[i]); cudaEventDestroy(downloaded[i]); }
+    cudaStreamDestroy(up);
+    cudaStreamDestroy(down);
+    for (int k = 0; k < 2; ++k) { pool_free(dF[k]); pool_free(dU[k]); }
+    return rc;
 }
 
 }  // extern "C"

@@ -163,18 +163,20 @@ const SegmentTable &segment_table(int rows, int n_strips, int resident_warps, in
 int g_tile_max_N = 1024;
 bool g_tile_even = false;
 int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
+int g_strip = 1;   // the bulk-copy 4-column kernel (mg_strip.cuh, instantiated in mg_legs.cu) for every even-sized pass; MG_STRIP=0: the round-1 kernels
 
-// Task geometry, persistent grid and launch shared by the two streaming kernels.
-template <typename Kernel>
-void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int min_ctas, int smem_bytes, bool err, int lead_rows,
-                          bool &opted_in)
+// Task geometry and persistent grid shared by the streaming kernels: fills the task fields of `p`, shifts the array
+// bases to global rows and returns the CTA count (0: nothing to launch).
+}  // namespace
+
+int stream_launch_prepare(StreamParams &p, int W, int warps, int min_ctas, bool err, int lead_rows)
 {
     Context &c = ctx();
     const int N = p.N;
     p.n_strips = (N + W - 1) / W;
     const int resident_warps = min_ctas * c.sm_count * warps;
     const SegmentTable &st = segment_table(p.own_hi - p.own_lo, p.n_strips, resident_warps, lead_rows, p.subset);
-    if (st.n == 0) return;                           // (an interior launch with nothing left to do)
+    if (st.n == 0) return 0;                         // (an interior launch with nothing left to do)
     p.segs = st.dev;
     p.n_segs = st.n;
     p.n_tasks = p.n_strips * p.n_segs;
@@ -186,9 +188,21 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
     if (p.Uout) p.Uout -= fine_shift;
     if (p.Fc) p.Fc -= (ptrdiff_t)p.fc_row0 * p.M;
     if (p.Uc) p.Uc -= (ptrdiff_t)p.uc_row0 * p.Nc;
-    const int blocks = std::max(1, std::min(min_ctas * c.sm_count, (p.n_tasks + warps - 1) / warps));
     if (err) p.partials = partials_buf((size_t)p.n_tasks);
     p.counter = c.counters + 8;   // [8] queue head, [9] finished warps (self-resetting)
+    return std::max(1, std::min(min_ctas * c.sm_count, (p.n_tasks + warps - 1) / warps));
+}
+
+namespace {
+
+template <typename Kernel>
+void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int min_ctas, int smem_bytes, bool err, int lead_rows,
+                          bool &opted_in)
+{
+    Context &c = ctx();
+    const int N = p.N;
+    const int blocks = stream_launch_prepare(p, W, warps, min_ctas, err, lead_rows);
+    if (blocks == 0) return;
     if (!opted_in) {
         check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(k_stream)");
         opted_in = true;
@@ -268,6 +282,7 @@ void launch_stream_s(int S, StreamParams &p)
 // mode: 0 plain, 1 ERR, 2 ERR+RES
 void launch_stream_any(int S, int in, int mode, StreamParams &p)
 {
+    if (g_strip && !tile_ok(p)) { launch_strip(S, in, mode, p); return; }
     if (in == IN_LOAD) {
         if (mode == 0) launch_stream_s<IN_LOAD, false, false>(S, p);
         else if (mode == 1) launch_stream_s<IN_LOAD, true, false>(S, p);
@@ -365,6 +380,7 @@ double *run_leg(int N, double L, const double *in, double *a, double *b, const d
             p.col_cell = t.col_cell;
             p.row_w = t.row_w;
             p.col_w = t.col_w;
+            p.row_info = t.row_info;
             p.c_dx = 1.0 / (double)(spec.Nc - 1);
             p.inv_c_dx = 1.0 / p.c_dx;
         }
@@ -408,7 +424,7 @@ int restrict_first_coarse_at_or_after(int N, int M, int fine_row)
 
 void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
                bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
-               const Slab *coarse_in, int subset)
+               const Slab *coarse_in, const PeerLinks &peers)
 {
     const Spacing sp = spacing(N, L);
     StreamParams p{};
@@ -418,8 +434,6 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
     p.own_lo = fine.own_lo;
     p.own_hi = fine.own_hi;
     p.raw_sum = 1;
-    p.subset = subset;
-    p.err_add = subset == 2 ? 1 : 0;             // the interior launch adds to the edge launch's sum
     p.h2 = sp.h2;
     p.inv_h2 = sp.inv_h2;
     p.F = F;
@@ -448,10 +462,14 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
         p.col_cell = t.col_cell;
         p.row_w = t.row_w;
         p.col_w = t.col_w;
+        p.row_info = t.row_info;
         p.c_dx = 1.0 / (double)(Nc - 1);
         p.inv_c_dx = 1.0 / p.c_dx;
     }
-    launch_stream_any(S, in_mode, mode, p);
+    p.peer_U_lo = peers.U_lo; p.peer_U_hi = peers.U_hi; p.u_lo_end = peers.u_lo_end; p.u_hi_begin = peers.u_hi_begin;
+    p.peer_Fc_lo = peers.Fc_lo; p.peer_Fc_hi = peers.Fc_hi; p.fc_lo_end = peers.fc_lo_end; p.fc_hi_begin = peers.fc_hi_begin;
+    p.flag_lo = peers.flag_lo; p.flag_hi = peers.flag_hi; p.flag_val = peers.flag_val;
+    launch_strip(S, in_mode, mode, p);       // slabs always take the peer-capable kernel
 }
 
 void fused_init()
@@ -462,6 +480,7 @@ void fused_init()
     if (const char *h = getenv("MG_SCHED_G")) g_sched_g = atof(h);     // <= 0: uniform segments
     if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
     if (const char *d = getenv("MG_COLS4")) g_cols4 = atoi(d);
+    if (const char *d = getenv("MG_STRIP")) g_strip = atoi(d);
     if (const char *d = getenv("MG_TILE_MAX_N")) { g_tile_max_N = std::max(0, atoi(d)); g_tile_even = true; }
 }
 

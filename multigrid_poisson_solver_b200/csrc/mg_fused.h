@@ -35,18 +35,34 @@ struct Slab {
 bool slab_pair_fusable(int N, int M);
 // smallest coarse row whose lower fine row (floor map of doRestriction) is >= fine_row; M if none
 int restrict_first_coarse_at_or_after(int N, int M, int fine_row);
+// Peer memory of a slab pass (k_strip): where the rows the neighbours keep as halos are ALSO stored, and the flag words
+// that tell them the pass has drained.  Pointers are the neighbours' arrays pre-offset to GLOBAL rows; null = no neighbour.
+struct PeerLinks {
+    double *U_lo = nullptr, *U_hi = nullptr;       // output rows < u_lo_end -> lower neighbour, rows >= u_hi_begin -> upper neighbour
+    int u_lo_end = 0, u_hi_begin = 0;
+    double *Fc_lo = nullptr, *Fc_hi = nullptr;     // the same for the rows of the restricted grid
+    int fc_lo_end = 0, fc_hi_begin = 0;
+    unsigned int *flag_lo = nullptr, *flag_hi = nullptr;
+    unsigned int flag_val = 0;
+};
 // One streaming pass (S <= 3 sweeps) on a slab.  in_mode: 0 load, 1 zero, 2 prolong (+add).
 // want_err: the slab's plain red-parity sum goes to *raw_err_dev.  coarse_out != null: restrict
 // the negated residual into the local F_c array of that coarse slab.  coarse_in: the local U_c.
 void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
                bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
-               const Slab *coarse_in, int subset = 0);
-// subset: 0 the whole slab; 1 only thin row segments at both ends of the owned range (they produce
-// every row the neighbours' halos need); 2 the interior in between (its error sum is ADDED to the
-// edge launch's).  1 followed by 2 is equivalent to 0.
+               const Slab *coarse_in, const PeerLinks &peers);
+void dist_release_on_shutdown();   // mgShutdown: the slab driver's arenas and cached source go with the context
 
 // Row segments {first, past-last} (relative to the first owned row) a fused pass over `rows` owned rows
 // hands to its warps, in queue order; host-only (no device state).  subset as in slab_pass.
 std::vector<int> segment_plan(int rows, int n_strips, int resident_warps, int lead_rows, int subset);
+
+// ---- launch plumbing shared by mg_fused.cu (round-1 kernels) and mg_legs.cu (k_strip)
+struct StreamParams;
+// fills the task fields of `p` (strips, row segments, queue, partials), shifts the array bases to global rows;
+// returns the CTA count of the persistent grid, 0 if there is nothing to launch
+int stream_launch_prepare(StreamParams &p, int W, int warps, int min_ctas, bool err, int lead_rows);
+// one fused pass with the 4-column bulk-copy kernel; in: 0 load, 1 zero, 2 prolong; mode: 0 plain, 1 ERR, 2 ERR+RES
+void launch_strip(int S, int in, int mode, StreamParams &p);
 
 }  // namespace mg

@@ -214,11 +214,12 @@ __global__ void __launch_bounds__(TX) k_restrict(int N, int M, int col_blocks, c
 }
 
 // ------------------------------------------------------------------ prolongation
-__global__ void k_prolong_table(int N, int M, int *row_cell, int *col_cell, double2 *row_w, double2 *col_w)
+__global__ void k_prolong_table(int N, int M, int *row_cell, int *col_cell, double2 *row_w, double2 *col_w, double4 *row_info)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= M) return;
     prolong_table_entry(t, N, M, row_cell[t], col_cell[t], row_w[t], col_w[t]);
+    row_info[t] = make_double4(row_w[t].x, row_w[t].y, (double)row_cell[t], 0.0);
 }
 
 template <bool ADD>
@@ -352,7 +353,8 @@ const ProlongTable &prolong_table(int N, int M)
     check(cudaMalloc(&t.col_cell, (size_t)M * sizeof(int)), "cudaMalloc prolong table");
     check(cudaMalloc(&t.row_w, (size_t)M * sizeof(double2)), "cudaMalloc prolong table");
     check(cudaMalloc(&t.col_w, (size_t)M * sizeof(double2)), "cudaMalloc prolong table");
-    MG_LAUNCH(k_prolong_table, (M + 255) / 256, 256, 0, N, M, t.row_cell, t.col_cell, t.row_w, t.col_w);
+    check(cudaMalloc(&t.row_info, (size_t)M * sizeof(double4)), "cudaMalloc prolong table");
+    MG_LAUNCH(k_prolong_table, (M + 255) / 256, 256, 0, N, M, t.row_cell, t.col_cell, t.row_w, t.col_w, t.row_info);
     return cache.emplace(std::make_pair(N, M), t).first->second;
 }
 

@@ -104,7 +104,19 @@ struct StreamParams {
     const double *Uc;
     const int *row_cell, *col_cell;
     const double2 *row_w, *col_w;
+    const double4 *row_info;   // [N] {row_w.x, row_w.y, row_cell, 0} (k_strip: one bulk copy per row)
     double c_dx, inv_c_dx;
+    // Row slabs with peer memory (k_strip only; all null / unused on one GPU).  The rows of the output a neighbour
+    // keeps as its halo are ALSO stored straight into the neighbour's array (pointers pre-offset to global rows like
+    // Uout / Fc): owned rows < u_lo_end go to the lower neighbour, owned rows >= u_hi_begin to the upper one; the same
+    // for the rows of the restricted grid.  When the launch has drained, its last CTA publishes `flag_val` in the
+    // neighbours' flag words (release at system scope) -- the consumer's stream waits for it before its next pass.
+    double *peer_U_lo, *peer_U_hi;
+    int u_lo_end, u_hi_begin;
+    double *peer_Fc_lo, *peer_Fc_hi;
+    int fc_lo_end, fc_hi_begin;
+    unsigned int *flag_lo, *flag_hi;
+    unsigned int flag_val;
 };
 
 template <int S, bool NEED_R, bool RES>
@@ -165,12 +177,19 @@ __device__ __forceinline__ void finish_launch(const StreamParams &p)
     __shared__ unsigned int fold_last;
     constexpr int T = WARPS * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (lane == 0) __threadfence();               // this warp's partials, before the CTA's ticket
+    const bool peers = p.flag_lo || p.flag_hi;
+    if (peers) __threadfence_system();            // every thread's halo rows in the neighbours' memory, before the ticket
+    else if (lane == 0) __threadfence();          // this warp's partials, before the CTA's ticket
     __syncthreads();                              // every warp of this CTA has drained the queue
     if (tid == 0) fold_last = atomicAdd(p.counter + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (!fold_last) return;
     __threadfence();
+    if (peers && tid == 0) {                      // all CTAs have fenced their peer stores: publish the pass number
+        __threadfence_system();
+        if (p.flag_lo) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_lo), "r"(p.flag_val) : "memory");
+        if (p.flag_hi) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_hi), "r"(p.flag_val) : "memory");
+    }
     if (ERR) {
         double s = 0.0;
         for (int k0 = tid; k0 < p.n_tasks; k0 += T * 16) {

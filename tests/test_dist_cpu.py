@@ -63,7 +63,7 @@ def fine_of_coarse(N, M):
     return f
 
 
-@pytest.mark.parametrize("N_max,world,threshold", [(16384, 8, 2048), (23168, 2, 2048), (46336, 8, 2048), (4096, 3, 256),
+@pytest.mark.parametrize("N_max,world,threshold", [(16384, 8, 2048), (23168, 2, 1024), (46336, 8, 1024), (32768, 4, 1024), (4096, 3, 256),
                                                    (1024, 4, 128), (32768, 4, 4096)])
 def test_plan_invariants(N_max, world, threshold):
     ladder = mg.cycles.ladder(N_max, 8)
@@ -96,15 +96,17 @@ def test_plan_invariants(N_max, world, threshold):
                 assert lo_cell >= cb[k] - HALO and hi_cell < cb[k + 1] + HALO
 
 
-def test_plan_rejects_odd_distributed_level():
+def test_plan_agglomerates_odd_levels_and_rejects_unfusable_pairs():
+    plan = mg.dist_plan([4098, 2049, 1024], 2, 1024)       # 2049 is odd: it and everything below run agglomerated
+    assert [lv["dist"] for lv in plan] == [True, False, False]
     with pytest.raises(mg.MGLibraryError):
-        mg.dist_plan([4098, 2049, 1024], 2, 1024)          # 2049 is odd but would have to be distributed
+        mg.dist_plan([4098, 4097], 2, 1024)                # N -> N-1 from a distributed level: no fused transfer (ratio < 1.2)
 
 
 def test_weak_scaling_sizes_are_servable():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
     for world, N in bench.WEAK_N.items():
-        plan = mg.dist_plan(mg.cycles.ladder(N, 8), world, 2048)
+        plan = mg.dist_plan(mg.cycles.ladder(N, 8), world, 1024)
         assert plan[0]["dist"] == (world > 1)
         assert abs(N * N / world / 16384 ** 2 - 1.0) < 0.01  # 16384^2 fine points per GPU

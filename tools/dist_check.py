@@ -32,7 +32,8 @@ def main():
     ok = True
     cases = [("V 2048", mg.cycles.v_cycle(2048, 8), 256), ("V 4096", mg.cycles.v_cycle(4096, 8), 1024),
              ("W 1024", mg.cycles.w_cycle(1024, 8, levels=4, step=2, tol=1e-7), 256),
-             ("trigger 1024", mg.cycles.v_cycle(1024, 8, step=-1), 256), ("V step5 1024", mg.cycles.v_cycle(1024, 16, step=5), 256)]
+             ("trigger 1024", mg.cycles.v_cycle(1024, 8, step=-1), 256), ("V step5 1024", mg.cycles.v_cycle(1024, 16, step=5), 256),
+             ("W 2048 x2 gathers", mg.cycles.w_cycle(2048, 8, levels=5, step=1, tol=1e-7), 1024), ("V 8192", mg.cycles.v_cycle(8192, 8), 1024)]
     for name, text, thr in cases:
         f = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False)
         f.write(text)
@@ -45,8 +46,8 @@ def main():
         same_U = np.array_equal(d["U_own"], one["U"][lo * N:hi * N])
         errs = all(abs(a["err"] - b["err"]) <= 1e-10 * max(abs(b["err"]), 1e-300) and a["steps"] == b["steps"]
                    for a, b in zip(d["trace"], one["trace"]) if b["node"] != 0)
-        mge = abs(d["mg_error"] - one["mg_error"]) <= 1e-10 * one["mg_error"] if rank == 0 or lo < hi else True
-        good = same_U and (errs or rank != 0) and mge
+        mge = abs(d["mg_error"] - one["mg_error"]) <= 1e-10 * one["mg_error"]
+        good = same_U and errs and mge and len(d["trace"]) == len(one["trace"])      # every rank holds the complete trace
         ok = ok and good
         print("rank %d %-14s rows [%d,%d) U_bit_identical=%s errors_ok=%s mg_error=%.12g (single %.12g) dist %.3f ms single %.3f ms"
               % (rank, name, lo, hi, same_U, errs, d["mg_error"], one["mg_error"], d["time_ms"], one["time_ms"]), flush=True)
