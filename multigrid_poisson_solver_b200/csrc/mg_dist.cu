@@ -328,7 +328,10 @@ __global__ void k_wait_gather(const unsigned int *words, int world, int self, un
 {
     const int s = threadIdx.x;
     if (s >= world || s == self) return;
-    const unsigned int *w = words + W_GATHER + s, *abort_w = words + W_ABORT;
+    const unsigned int *w = words + W_GATHER + s;
+    unsigned int *abort_w = const_cast<unsigned int *>(words) + W_ABORT;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
         unsigned int v, a;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
@@ -336,6 +339,8 @@ __global__ void k_wait_gather(const unsigned int *words, int world, int self, un
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(abort_w) : "memory");
         if (a) break;
         __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) { *abort_w = 2u; break; }   // 20 s without the peer's rows: give up instead of holding the GPU (reported as an error)
     }
 }
 
@@ -1057,6 +1062,11 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
     if (c.err_code && rc == 0) rc = 10;
     if (rc) fab.abort_peers(c.stream);           // the other ranks must not wait for passes that will never come
     harvest();
+    if (comm.world > 1) {                        // did a peer give up (or a gather wait time out)?
+        unsigned int aborted = 0;
+        check(cudaMemcpy(&aborted, fab.peer[cy.ranks[0].rank].words + W_ABORT, sizeof aborted, cudaMemcpyDeviceToHost), "D2H abort word");
+        if (aborted && rc == 0) { fail(-42, aborted == 2 ? "slab driver: timed out waiting for a peer's rows" : "slab driver: a peer rank reported an error"); rc = 31; }
+    }
     const auto wall1 = std::chrono::steady_clock::now();
     for (size_t i = 1; i < marks.size(); ++i) {
         float ms = 0.f;

@@ -55,3 +55,12 @@ void launch_strip(int S, int in, int mode, StreamParams &p)
 }
 
 }  // namespace mg
+
+#ifdef MG_SP_DEBUG
+extern "C" void mgStripDebug(unsigned long long *out64, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out64, mg::g_strip_dbg, 64 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[64] = {}; cudaMemcpyToSymbol(mg::g_strip_dbg, z, sizeof z); }
+}
+#endif

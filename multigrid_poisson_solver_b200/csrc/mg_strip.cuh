@@ -80,6 +80,9 @@ __host__ __device__ constexpr int strip_warp_bytes(int in, bool res)
 __host__ __device__ constexpr int strip_smem_bytes(int in, bool res) { return SP_WARPS * strip_warp_bytes(in, res); }
 
 struct d4 { double v[4]; };
+#ifdef MG_SP_DEBUG
+__device__ unsigned long long g_strip_dbg[64];
+#endif
 
 __device__ __forceinline__ d4 lds4(unsigned addr)
 {
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, strip_min_ctas(IN, RES)) k_stri
     if (lane == 0) task = (int)atomicAdd(p.counter, 1u);
     task = __shfl_sync(FULL, task, 0);
     if (task >= p.n_tasks) break;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();                                        // the previous task's last reads of the ring precede this task's copies
     const int seg = task / p.n_strips;                   // consecutive tasks = adjacent strips of one row segment
     const int strip = task - seg * p.n_strips;
@@ -322,6 +326,30 @@ __global__ void __launch_bounds__(SP_WARPS * 32, strip_min_ctas(IN, RES)) k_stri
             for (int q = 0; q < 4; ++q) x.v[q] = f_new.v[q] = 0.0;
             if (IN == IN_LOAD) x = lds4(rd + k * SP_SLOT);
             if (NF > 0) f_new = lds4(rd + k * SP_SLOT + 1024);
+#ifdef MG_SP_DEBUG
+            if (IN == IN_LOAD && FAST) {                 // what did the ring hand out?  compare with global memory
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double g = __ldcg(p.Uin + (ptrdiff_t)r * ldn + cx + q);
+                    if (g != x.v[q]) {
+                        const double prev = __ldcg(p.Uin + (ptrdiff_t)(r - 4) * ldn + cx + q), next = __ldcg(p.Uin + (ptrdiff_t)(r + 4) * ldn + cx + q);
+                        const int kind = x.v[q] == prev ? 1 : x.v[q] == next ? 2 : 3;
+                        atomicAdd(&g_strip_dbg[kind], 1ull);
+                        __nanosleep(2000);
+                        const double again = lds1(rd + k * SP_SLOT + 8 * q);
+                        atomicAdd(&g_strip_dbg[again == g ? 4 : again == x.v[q] ? 5 : 6], 1ull);
+                        atomicAdd(&g_strip_dbg[8 + (rb == r_first ? 0 : 1)], 1ull);          // first chunk of a task or later
+                        atomicAdd(&g_strip_dbg[10 + k], 1ull);
+                        if (atomicAdd(&g_strip_dbg[0], 1ull) < 8) {
+                            g_strip_dbg[16 + 0] = (unsigned long long)task; g_strip_dbg[16 + 1] = r; g_strip_dbg[16 + 2] = lane; g_strip_dbg[16 + 3] = r_first;
+                            g_strip_dbg[16 + 4] = r_end; g_strip_dbg[16 + 5] = phase;
+                        }
+                    }
+                    const double gf = __ldcg(p.F + (ptrdiff_t)(r - 1) * ldn + cx + q);
+                    if (gf != f_new.v[q]) atomicAdd(&g_strip_dbg[7], 1ull);
+                }
+            }
+#endif
             if (IN == IN_PROLONG && (FAST || r <= N - 1)) {
                 // level 0 of the 1 node: U_f + P(U_c) (:700 + :569)
                 const d4 uf = lds4(rd + k * SP_SLOT);
@@ -350,13 +378,12 @@ __global__ void __launch_bounds__(SP_WARPS * 32, strip_min_ctas(IN, RES)) k_stri
                     for (int q = 0; q < 4; ++q) x.v[q] = __dadd_rn(uf.v[q], __ddiv_rn(__ddiv_rn(v.v[q], d), d));
                 }
             }
-#ifdef MG_SP_FENCE
+            // Every lane has read slot k: refill it with row r + DEPTH.  The reads went through the generic proxy, the
+            // copy writes through the async proxy: without the proxy fence the copy may overtake them (measured on
+            // B200: a plain S = 1 pass at N = 2048 handed out rows of the NEXT occupant in 20 of 25 runs).
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-            __syncwarp();                                // every lane has read slot k: refill it with row r + DEPTH
-#ifndef MG_SP_LATE_ISSUE
+            __syncwarp();
             issue(k, !FAST);
-#endif
 
             if (NF > 0) fr[k % NR] = f_new;
 
@@ -479,9 +506,6 @@ __global__ void __launch_bounds__(SP_WARPS * 32, strip_min_ctas(IN, RES)) k_stri
                     d_prev = d_cur;
                 }
             }
-#ifdef MG_SP_LATE_ISSUE
-            issue(k, !FAST);
-#endif
         }
         phase ^= 1u;
     };
