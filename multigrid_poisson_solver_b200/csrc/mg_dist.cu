@@ -737,17 +737,17 @@ int plan_arena(const std::vector<double> &tok, const Header &h, int world, int t
     std::vector<std::vector<size_t>> tops;       // per level: tops before its allocation
     std::vector<size_t> top((size_t)world, 0), peak((size_t)world, 0);
     gather_need = 0;
-    auto push = [&](const LevelGeom &g, bool has_own_F) {
+    auto push = [&](const LevelGeom &g) {          // U, W and F slabs (the top level's F may be the caller's: planned anyway)
         tops.push_back(top);
         geom.push_back(g);
         if (g.dist)
             for (int r = 0; r < world; ++r) {
-                top[r] += (has_own_F ? 3 : 2) * slab_bytes(g, r);
+                top[r] += 3 * slab_bytes(g, r);
                 peak[r] = std::max(peak[r], top[r]);
             }
     };
     auto pop = [&]() { top = tops.back(); tops.pop_back(); geom.pop_back(); };
-    push(top_geometry(h.N_max, world, threshold), false);
+    push(top_geometry(h.N_max, world, threshold));
     size_t cur = h.first_node, pos = 0;
     int init = 1, n_recs = 0;
     std::string why;
@@ -774,7 +774,7 @@ int plan_arena(const std::vector<double> &tok, const Header &h, int world, int t
             LevelGeom coarse;
             if (!induce_geometry(geom.back(), next_N, world, threshold, coarse, why)) return 20;
             if (!coarse.dist) gather_need = std::max(gather_need, ((size_t)next_N * next_N * sizeof(double) + 255) / 256 * 256);
-            push(coarse, true);
+            push(coarse);
         } else if (node == 0) {
             return 21;                           // an exact solve on a distributed level
         } else if (node == 1) {
