@@ -645,7 +645,7 @@ def dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, unfu
         kernels.append(entry("down_leg", "k_stream<3,IN_ZERO,ERR,RES> (-1 node: 3 sweeps+error+residual+negate+restrict)", ms,
                              16.0 * n + 8.0 * m, "F in, U out, F_c out (unfused sequence moves 146 B/point)"))
         ms = timeit(lambda: lib.mgSmooth(N, 1.0, U.ptr, F.ptr, 3, W.ptr, slot))
-        kernels.append(entry("smooth_S3", "k_stream4<3,IN_LOAD,ERR> (doSmoothing step=3: 3 sweeps+error)", ms, 24.0 * n,
+        kernels.append(entry("smooth_S3", "k_strip<3,IN_LOAD,ERR> (doSmoothing step=3: 3 sweeps+error; 4 columns per lane, bulk copies + mbarriers)", ms, 24.0 * n,
                              "U in, F in, U out (unfused sequence moves 88 B/point)"))
     top = kernels[0]
     return {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved"], "peak": hbm_peak, "unit": "GB/s",

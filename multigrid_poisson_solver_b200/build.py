@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, os.environ.get("MG_LIB_NAME", "libmgb200.so"))   # MG_LIB_NAME: tuning variants next to the product library
 EXE = os.path.join(HERE, "MG_GPU")
-SOURCES = ["mg_abi.cu", "mg_kernels.cu", "mg_fused.cu", "mg_legs.cu", "mg_exact.cu", "mg_dist.cu", "mg_tail.cu", "mg_driver.cpp"]
+SOURCES = ["mg_abi.cu", "mg_kernels.cu", "mg_fused.cu", "mg_legs.cu", "mg_peer.cu", "mg_exact.cu", "mg_dist.cu", "mg_tail.cu", "mg_driver.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

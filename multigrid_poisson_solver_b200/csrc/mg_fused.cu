@@ -163,7 +163,8 @@ const SegmentTable &segment_table(int rows, int n_strips, int resident_warps, in
 int g_tile_max_N = 1024;
 bool g_tile_even = false;
 int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
-int g_strip = 1;   // the bulk-copy 4-column kernel (mg_strip.cuh, instantiated in mg_legs.cu) for every even-sized pass; MG_STRIP=0: the round-1 kernels
+int g_strip = 1;   // the bulk-copy 4-column kernel (mg_strip.cuh, instantiated in mg_legs.cu) for smoothing passes; MG_STRIP=0: never
+int g_strip_min_N = 8192;   // ... from this grid size on (MG_STRIP_MIN_N)
 
 // Task geometry and persistent grid shared by the streaming kernels: fills the task fields of `p`, shifts the array
 // bases to global rows and returns the CTA count (0: nothing to launch).
@@ -253,7 +254,7 @@ void launch_stream(StreamParams &p)
     if (tile_ok(p)) { launch_tile<S, IN, ERR, RES>(p); return; }
     // Measured on B200 (N = 16384): 4 columns per lane win for the passes without restriction (smoothing
     // pass 1.05 vs 1.09 ms); with restriction the 230-254 registers leave 8 warps per SM and lose (1.40 vs 1.22 ms).
-    if (IN != IN_PROLONG && !RES && g_cols4) {
+    if (IN != IN_PROLONG && !RES && g_cols4 && !(p.flag_lo || p.flag_hi)) {
         // instantiated only for IN_LOAD / IN_ZERO (the branch is dead for IN_PROLONG)
         constexpr int IN4 = IN == IN_PROLONG ? IN_LOAD : IN;
         using G4 = Stream4Geo<S, ERR || RES, RES>;
@@ -282,7 +283,14 @@ void launch_stream_s(int S, StreamParams &p)
 // mode: 0 plain, 1 ERR, 2 ERR+RES
 void launch_stream_any(int S, int in, int mode, StreamParams &p)
 {
-    if (g_strip && !tile_ok(p)) { launch_strip(S, in, mode, p); return; }
+    // Which streaming kernel (all bit-identical; measured on B200): the 4-column bulk-copy kernel (k_strip) wins
+    // for passes WITHOUT restriction / prolongation on large grids (HBM bound: 0.93 of the measured peak against 0.87); the
+    // -1 and 1 nodes are issue bound and need the 12-16 warps per SM only the 2-column kernel (k_stream) leaves room for.
+    // Slab passes with peer memory: k_strip or k_stream (k_stream4 has no peer stores).
+    const bool peers = p.flag_lo || p.flag_hi;
+    const bool plain_pass = in != IN_PROLONG && mode != 2;
+    if (g_strip && !tile_ok(p) && plain_pass && (p.N >= g_strip_min_N || peers)) { launch_strip(S, in, mode, p); return; }
+    if (peers) { launch_stream_peer(S, in, mode, p); return; }
     if (in == IN_LOAD) {
         if (mode == 0) launch_stream_s<IN_LOAD, false, false>(S, p);
         else if (mode == 1) launch_stream_s<IN_LOAD, true, false>(S, p);
@@ -469,7 +477,7 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
     p.peer_U_lo = peers.U_lo; p.peer_U_hi = peers.U_hi; p.u_lo_end = peers.u_lo_end; p.u_hi_begin = peers.u_hi_begin;
     p.peer_Fc_lo = peers.Fc_lo; p.peer_Fc_hi = peers.Fc_hi; p.fc_lo_end = peers.fc_lo_end; p.fc_hi_begin = peers.fc_hi_begin;
     p.flag_lo = peers.flag_lo; p.flag_hi = peers.flag_hi; p.flag_val = peers.flag_val;
-    launch_strip(S, in_mode, mode, p);       // slabs always take the peer-capable kernel
+    launch_stream_any(S, in_mode, mode, p);
 }
 
 void fused_init()
@@ -481,6 +489,7 @@ void fused_init()
     if (const char *d = getenv("MG_NO_STREAM")) g_disable = atoi(d) != 0;
     if (const char *d = getenv("MG_COLS4")) g_cols4 = atoi(d);
     if (const char *d = getenv("MG_STRIP")) g_strip = atoi(d);
+    if (const char *d = getenv("MG_STRIP_MIN_N")) g_strip_min_N = atoi(d);
     if (const char *d = getenv("MG_TILE_MAX_N")) { g_tile_max_N = std::max(0, atoi(d)); g_tile_even = true; }
 }
 

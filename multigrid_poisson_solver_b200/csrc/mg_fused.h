@@ -64,5 +64,7 @@ struct StreamParams;
 int stream_launch_prepare(StreamParams &p, int W, int warps, int min_ctas, bool err, int lead_rows);
 // one fused pass with the 4-column bulk-copy kernel; in: 0 load, 1 zero, 2 prolong; mode: 0 plain, 1 ERR, 2 ERR+RES
 void launch_strip(int S, int in, int mode, StreamParams &p);
+// the -1 node (in 0 / 1, mode 2) or the 1 node (in 2, mode 0 / 1) on a slab with peer memory (mg_peer.cu)
+void launch_stream_peer(int S, int in, int mode, StreamParams &p);
 
 }  // namespace mg

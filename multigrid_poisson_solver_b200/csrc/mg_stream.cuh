@@ -39,6 +39,12 @@ enum { IN_LOAD = 0, IN_ZERO = 1, IN_PROLONG = 2 };
 #ifndef MG_STREAM_DEPTH
 #define MG_STREAM_DEPTH 4
 #endif
+#ifndef MG_ZERO_SHORTCUT
+#define MG_ZERO_SHORTCUT 1       // IN_ZERO: first sweep without stencil
+#endif
+#ifndef MG_RES_EVEN
+#define MG_RES_EVEN 1            // restriction: nested ladders skip the odd column
+#endif
 // CTA shape per variant (measured on B200, N = 16384): passes without restriction run best as
 // 4-warp CTAs, three per SM (12 warps, up to 168 registers, no spills); the -1 node (RES) as
 // 8-warp CTAs, two per SM (16 warps, 128 registers).
@@ -292,7 +298,9 @@ __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0
 template <bool B>
 struct BoolTag { static constexpr bool value = B; };
 
-template <int S, int IN, bool ERR, bool RES>
+// PEER: row slabs with peer memory -- the rows a neighbouring GPU keeps as its halo are also stored straight into its
+// array (a separate instantiation, mg_peer.cu: the single-GPU kernels sit exactly at their register limits).
+template <int S, int IN, bool ERR, bool RES, bool PEER = false>
 __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES).min_ctas) k_stream(const StreamParams p)
 {
     constexpr int STREAM_WARPS = stream_shape(RES).warps;
@@ -347,6 +355,8 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     const int own_r_lo = p.own_lo + seg_rows.x, own_r_hi = p.own_lo + seg_rows.y;
     const int r_first = max(0, own_r_lo - G::ROW_LEAD);
     const int r_last = min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD);
+    // rows of this task whose output is also a neighbour's halo (slabs with peer memory)
+    const bool peer_rows = PEER && ((p.peer_U_lo && own_r_lo < p.u_lo_end) || (p.peer_U_hi && own_r_hi > p.u_hi_begin));
 
     // Register state.  Every index below is a compile-time constant after unrolling, so the
     // arrays live in registers and rotate by renaming, not by moves.
@@ -373,6 +383,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         zx = ccx == 0 || ccx == p.M - 1;
         zy = ccy == 0 || ccy == p.M - 1;
     }
+    const bool res_even = MG_RES_EVEN && RES && __all_sync(0xffffffffu, ccy < 0);   // nested ladder: coarse points at even fine columns only
     if (RES && active) {
         const int f0 = r_first - S - 2;           // the fine row step r_first pairs with the one above it
         if (f0 >= 0 && f0 <= N - 1) rinfo_next = p.rrow[f0];
@@ -553,25 +564,44 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
 #pragma unroll
             for (int t = 0; t < S; ++t) {
                 const int i = r - t - 1;
-                const double2 below = w[t][k & 1], c = w[t][(k & 1) ^ 1];
                 const double2 f = fr[(k - t + 4 * NR) % NR];
-                const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
                 double2 nx;
-                nx.x = jacobi_fast(c.x, sum4(x.x, below.x, c.y, left), __dmul_rn(h2, f.x));
-                nx.y = jacobi_fast(c.y, sum4(x.y, below.y, right, c.x), __dmul_rn(h2, f.y));
-                if (!FAST) {                                      // boundary rows / columns are carried over
-                    const bool row_in = i > 0 && i < N - 1;
-                    nx.x = (row_in && x_in) ? nx.x : c.x;
-                    nx.y = (row_in && y_in) ? nx.y : c.y;
+                if (MG_ZERO_SHORTCUT && IN == IN_ZERO && t == 0) {
+                    // level 0 is all zeros: jacobi_at(0, 0, h2 f) = 0 + 0.25*((0 - 0) - h2 f) with the same roundings -- no
+                    // stencil, no shuffles, no level-0 window
+                    nx.x = __dadd_rn(0.0, __dmul_rn(0.25, __dsub_rn(0.0, __dmul_rn(h2, f.x))));
+                    nx.y = __dadd_rn(0.0, __dmul_rn(0.25, __dsub_rn(0.0, __dmul_rn(h2, f.y))));
+                    if (!FAST) {
+                        const bool row_in = i > 0 && i < N - 1;
+                        nx.x = (row_in && x_in) ? nx.x : 0.0;
+                        nx.y = (row_in && y_in) ? nx.y : 0.0;
+                    }
+                } else {
+                    const double2 below = w[t][k & 1], c = w[t][(k & 1) ^ 1];
+                    const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
+                    nx.x = jacobi_fast(c.x, sum4(x.x, below.x, c.y, left), __dmul_rn(h2, f.x));
+                    nx.y = jacobi_fast(c.y, sum4(x.y, below.y, right, c.x), __dmul_rn(h2, f.y));
+                    if (!FAST) {                                  // boundary rows / columns are carried over
+                        const bool row_in = i > 0 && i < N - 1;
+                        nx.x = (row_in && x_in) ? nx.x : c.x;
+                        nx.y = (row_in && y_in) ? nx.y : c.y;
+                    }
+                    w[t][k & 1] = x;
                 }
-                w[t][k & 1] = x;
                 x = nx;
             }
 
             // ---- x is now level S, row r-S
             {
                 const int i = r - S;
-                if (Op && i >= own_r_lo && i < own_r_hi && col_own) *reinterpret_cast<double2 *>(Op + (ptrdiff_t)i * ldn + cx) = x;
+                if (Op && i >= own_r_lo && i < own_r_hi && col_own) {
+                    const ptrdiff_t o = (ptrdiff_t)i * ldn + cx;
+                    *reinterpret_cast<double2 *>(Op + o) = x;
+                    if (PEER && peer_rows) {             // slabs with peer memory: the same row into the neighbour's halo
+                        if (p.peer_U_lo && i < p.u_lo_end) *reinterpret_cast<double2 *>(p.peer_U_lo + o) = x;
+                        if (p.peer_U_hi && i >= p.u_hi_begin) *reinterpret_cast<double2 *>(p.peer_U_hi + o) = x;
+                    }
+                }
             }
 
             if (NEED_R) {
@@ -601,13 +631,29 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                     if (FAST || (f_row + 1 >= 0 && f_row + 1 <= N - 1)) rinfo_next = p.rrow[f_row + 1];
                     else rinfo_next = make_double2(-1.0, 0.0);
                     const int crow = (int)ri.x;
-                    if (crow >= 0 && f_row >= own_r_lo && f_row < own_r_hi) {
+                    if (crow >= 0 && f_row >= own_r_lo && f_row < own_r_hi) {   // warp-uniform
                         const double cw = ri.y;
-                        const double np = shfl_dn1(d_prev.x), nc = shfl_dn1(d_cur.x);
                         const bool row_edge = crow == 0 || crow == p.M - 1;
-                        double *out = p.Fc + (ptrdiff_t)crow * p.M;
-                        if (ccx >= 0) out[ccx] = (row_edge || zx) ? 0.0 : restrict_at(d_prev.x, d_prev.y, d_cur.x, d_cur.y, ax, cw);
-                        if (ccy >= 0) out[ccy] = (row_edge || zy) ? 0.0 : restrict_at(d_prev.y, np, d_cur.y, nc, ay, cw);
+                        const ptrdiff_t ro = (ptrdiff_t)crow * p.M;
+                        double *out = p.Fc + ro;
+                        // slabs with peer memory: a coarse row a neighbour keeps as its halo also goes straight into its array
+                        double *peer_lo = (PEER && p.peer_Fc_lo && crow < p.fc_lo_end) ? p.peer_Fc_lo + ro : nullptr;
+                        double *peer_hi = (PEER && p.peer_Fc_hi && crow >= p.fc_hi_begin) ? p.peer_Fc_hi + ro : nullptr;
+                        if (ccx >= 0) {
+                            const double val = (row_edge || zx) ? 0.0 : restrict_at(d_prev.x, d_prev.y, d_cur.x, d_cur.y, ax, cw);
+                            out[ccx] = val;
+                            if (PEER && peer_lo) peer_lo[ccx] = val;
+                            if (PEER && peer_hi) peer_hi[ccx] = val;
+                        }
+                        if (!res_even) {                 // (nested ladders: no lane has a coarse point at its odd column)
+                            const double np = shfl_dn1(d_prev.x), nc = shfl_dn1(d_cur.x);
+                            if (ccy >= 0) {
+                                const double val = (row_edge || zy) ? 0.0 : restrict_at(d_prev.y, np, d_cur.y, nc, ay, cw);
+                                out[ccy] = val;
+                                if (PEER && peer_lo) peer_lo[ccy] = val;
+                                if (PEER && peer_hi) peer_hi[ccy] = val;
+                            }
+                        }
                     }
                     d_prev = d_cur;
                 }

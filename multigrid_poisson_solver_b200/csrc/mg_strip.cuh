@@ -55,10 +55,10 @@ constexpr int SP_WARPS = 4;            // warps per CTA
 constexpr int SP_SLOT = 2048;          // one row of the ring: [U row segment 1 KiB | F row segment 1 KiB]; 4 rows = 2 pair slots in flight
 // CTAs per SM (register budget 65536 / (128 * CTAs)): tuned on B200, see DESIGN.md
 #ifndef MG_SP_CTAS_PLAIN
-#define MG_SP_CTAS_PLAIN 3
+#define MG_SP_CTAS_PLAIN 2
 #endif
 #ifndef MG_SP_CTAS_RES
-#define MG_SP_CTAS_RES 3
+#define MG_SP_CTAS_RES 2
 #endif
 #ifndef MG_SP_CTAS_PROLONG
 #define MG_SP_CTAS_PROLONG 2
