@@ -114,6 +114,18 @@ void mgExactSolve(int N, double L, double *U, double *F, double target_error, in
 double *mgUpLeg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, double *F, int step,
                 double *error_slot);
 
+/* The error-trigger forms of the two nodes (con_step = -1, MG_solver_CPU.cpp:194-240 and :376-408): sweep, evaluate the
+ * smoothing error, stop when two successive errors differ by <= 0.01 (at least two sweeps).  Two sweeps per launch, the
+ * launch reporting the error after each of them; every launch of the -1 node also restricts its result, so a node that
+ * stops at the minimum of two sweeps is one launch and one synchronisation.  If the loop ends after an odd number of
+ * sweeps the last launch is repeated with a single sweep from the same input.  *steps = sweeps done, *error = the last
+ * smoothing error (host pointers, valid on return).  Returns the buffer holding the result (U / U_f or U_work), or NULL if
+ * the size is not served by the streaming kernel (odd N, ...): the caller then sweeps one at a time with mgSmooth. */
+double *mgDownLegTrigger(int N, double L, double *U, double *U_work, double *F, int zero_init, int M, double *F_c,
+                         int *steps, double *error);
+double *mgUpLegTrigger(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, double *F, int *steps,
+                       double *error);
+
 /* The coarse tail of a cycle in one kernel: a node sub-stream that starts at a level of at most
  * mgCoarseTailMaxN() points per side and returns to it (parallel arrays, one entry per node:
  * kind -1/0/1, step (-1 = error trigger), zero_init, the size the node works on, next_N for -1

@@ -60,6 +60,8 @@ ABI = {
     "mgDownLeg": (_vp, [C.c_int, C.c_double, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _dp]),
     "mgExactSolve": (None, [C.c_int, C.c_double, _vp, _vp, C.c_double, C.c_int, _dp]),
     "mgUpLeg": (_vp, [C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, C.c_int, _dp]),
+    "mgDownLegTrigger": (_vp, [C.c_int, C.c_double, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int), _dp]),
+    "mgUpLegTrigger": (_vp, [C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, C.POINTER(C.c_int), _dp]),
     "mgCoarseTailMaxN": (C.c_int, []),
     "mgCoarseTailMaxOps": (C.c_int, []),
     "mgCoarseTail": (C.c_int, [C.c_double, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp]),

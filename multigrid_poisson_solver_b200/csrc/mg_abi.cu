@@ -370,6 +370,19 @@ double *mgUpLeg(int Nc, const double *U_c, int N, double L, double *U_f, double 
     return up_leg(Nc, U_c, N, L, U_f, U_work, F, step, slot_device_ptr(error_slot));
 }
 
+double *mgDownLegTrigger(int N, double L, double *U, double *U_work, double *F, int zero_init, int M, double *F_c, int *steps,
+                         double *error)
+{
+    if (!ensure_ready() || !trigger_fusable_down(N, M)) return nullptr;
+    return down_leg_trigger(N, L, U, U_work, F, zero_init != 0, M, F_c, steps, error);
+}
+
+double *mgUpLegTrigger(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, double *F, int *steps, double *error)
+{
+    if (!ensure_ready() || !trigger_fusable_up(Nc, N)) return nullptr;
+    return up_leg_trigger(Nc, U_c, N, L, U_f, U_work, F, steps, error);
+}
+
 int mgPrint2File(int N, const double *U_host, const char *file_name)
 {
     FILE *out = fopen(file_name, "w");

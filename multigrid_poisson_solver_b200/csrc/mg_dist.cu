@@ -605,7 +605,7 @@ public:
     // straight into their arenas; the pass number is published when the launch has drained.
     void pass(int li, double L, int S, int in_mode, bool want_err, int scal_idx, int M, bool with_fc, bool fc_dist,
               const std::vector<int> &cb, const std::vector<double *> &fc_full, int Nc, const std::vector<const double *> &uc,
-              const std::vector<Slab> &uc_slab)
+              const std::vector<Slab> &uc_slab, bool mid = false)
     {
         const LevelGeom &g = geom[li];
         const bool writes_U = !(S == 0 && in_mode == 0);
@@ -643,13 +643,24 @@ public:
                     fc = fc_full[i];
                 }
             }
-            slab_pass(g.N, L, S, in_mode, l.U, l.F, writes_U ? l.W : nullptr, l.slab, want_err, ranks[i].scal + scal_idx, M, fc,
-                      with_fc ? &fcs : nullptr, Nc, uc.empty() ? nullptr : uc[i], uc.empty() ? nullptr : &uc_slab[i], pl);
+            if (mid)     // a pass of an error-trigger loop: S = 2 with both errors (scal[idx] last, scal[idx+1] first sweep) or S = 1
+                slab_trigger_pass(g.N, L, S, in_mode, l.U, l.F, l.W, l.slab, ranks[i].scal + scal_idx, M, fc, with_fc ? &fcs : nullptr, Nc,
+                                  uc.empty() ? nullptr : uc[i], uc.empty() ? nullptr : &uc_slab[i], pl);
+            else
+                slab_pass(g.N, L, S, in_mode, l.U, l.F, writes_U ? l.W : nullptr, l.slab, want_err, ranks[i].scal + scal_idx, M, fc,
+                          with_fc ? &fcs : nullptr, Nc, uc.empty() ? nullptr : uc[i], uc.empty() ? nullptr : &uc_slab[i], pl);
         }
         if (writes_U) {
             for (auto &st : ranks) std::swap(st.lv[li].U, st.lv[li].W);
             std::swap(alloc[li].U, alloc[li].W);
         }
+    }
+
+    // the last pass went one sweep too far (trigger loop): its input becomes the current grid again
+    void unswap(int li)
+    {
+        for (auto &st : ranks) std::swap(st.lv[li].U, st.lv[li].W);
+        std::swap(alloc[li].U, alloc[li].W);
     }
 
     // Agglomeration boundary: every rank sends its rows [cb[r], cb[r+1]) of the M x M restricted grid (already in its own
@@ -899,25 +910,47 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
         check(cudaStreamSynchronize(c.stream), "sync");
         return s;
     };
-    // the error-trigger loop on a distributed level (:216-230 / :388-402): one sweep per pass, the all-reduced error decides
-    auto trigger_loop = [&](int li, bool first_from_zero, int N, int &done, double &err_host) {
-        double slope = TRIGGER + 1.0, prev = 0.0;
-        done = 0;
-        while (slope > TRIGGER) {
-            const int idx = next_scal();
-            cy.pass(li, L, 1, (done == 0 && first_from_zero) ? 1 : 0, true, idx, 0, false, false, {}, {}, 0, {}, {});
-            const double s = reduced_now(idx);
-            err_host = (s + s) / N / N;
-            ++done;
-            if (done > 1) slope = std::fabs(err_host - prev);
-            prev = err_host;
-            if (c.err_code) break;
-        }
-    };
     const std::vector<const double *> no_uc;
     const std::vector<Slab> no_slab;
     const std::vector<double *> no_fc;
     const std::vector<int> no_cb;
+    // The error-trigger loop on a distributed level (:216-230 / :388-402), two sweeps per pass: the pass reports the error after
+    // each of its sweeps, both are all-reduced, every rank takes the same decision.  If the loop ends after an odd number of
+    // sweeps the last pass is repeated with one sweep from the same input.  With a coarse level (M > 0) every pass restricts
+    // its result speculatively, so a -1 node whose trigger fires at the minimum of two sweeps costs one pass.
+    auto trigger_loop = [&](int li, int first_mode, int N, int M, bool with_fc, bool fc_dist, const std::vector<int> &cb,
+                            const std::vector<double *> &fc_full, int Nc, const std::vector<const double *> &uc, const std::vector<Slab> &uc_slab,
+                            int &done, double &err_host) {
+        double prev = 0.0;
+        int mode = first_mode;
+        done = 0;
+        for (;;) {
+            if (cy.scal_used_ + 2 > SCAL_BATCH) harvest();
+            const int idx = cy.scal_used_;
+            cy.scal_used_ += 2;
+            cy.pass(li, L, 2, mode, true, idx, M, with_fc, fc_dist, cb, fc_full, mode == 2 ? Nc : 0, mode == 2 ? uc : no_uc, mode == 2 ? uc_slab : no_slab, true);
+            cy.allreduce(idx, 2);
+            double s[2] = {0.0, 0.0};
+            check(cudaMemcpyAsync(s, cy.ranks[0].scal + idx, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+            check(cudaStreamSynchronize(c.stream), "sync");
+            if (c.err_code) break;
+            const double e2 = (s[0] + s[0]) / N / N, e1 = (s[1] + s[1]) / N / N;
+            if (done + 1 > 1 && std::fabs(e1 - prev) <= TRIGGER) {       // the loop ends after the first of these two sweeps
+                cy.unswap(li);
+                const int j = next_scal();
+                cy.pass(li, L, 1, mode, true, j, M, with_fc, fc_dist, cb, fc_full, mode == 2 ? Nc : 0, mode == 2 ? uc : no_uc, mode == 2 ? uc_slab : no_slab, true);
+                const double r = reduced_now(j);
+                done += 1;
+                err_host = (r + r) / N / N;
+                break;
+            }
+            done += 2;
+            mode = 0;
+            err_host = e2;
+            if (std::fabs(e2 - e1) <= TRIGGER) break;
+            prev = e2;
+        }
+    };
 
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
@@ -988,10 +1021,9 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
             int done = step;
             double err_host = 0.0;
             bool host_err = false;
-            if (step == -1) {           // :194-240: trigger loop, then the residual + restriction of the result
-                trigger_loop(li, zero_init, fine.N, done, err_host);
+            if (step == -1) {           // :194-240: trigger loop; the pass that ends it has also restricted its residual
+                trigger_loop(li, zero_init ? 1 : 0, fine.N, next_N, true, coarse.dist, cb, fc_full, 0, no_uc, no_slab, done, err_host);
                 host_err = true;
-                cy.pass(li, L, 0, 0, false, 0, next_N, true, coarse.dist, cb, fc_full, 0, no_uc, no_slab);
             } else {
                 // step > 0: passes of at most 3 sweeps, the last one also restricts.  step < -1 (:244-259): doSmoothing with a
                 // negative count = no sweep; the grid is still zeroed, the error evaluated, the residual restricted.
@@ -1033,6 +1065,16 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
             std::vector<Slab> uc_slab(cy.ranks.size());
             for (size_t i = 0; i < cy.ranks.size(); ++i) { uc[i] = cy.ranks[i].lv[lc].U; uc_slab[i] = cy.ranks[i].lv[lc].slab; }
 
+            if (step == -1) {            // prolongation + the trigger loop, two sweeps per pass
+                int done = 0;
+                double err_host = 0.0;
+                trigger_loop(lf, 2, fine.N, 0, false, false, no_cb, no_fc, coarse.N, uc, uc_slab, done, err_host);
+                record(1, fine.N, done, err_host);
+                if (!quiet) fputs(kProlongArt, stdout);
+                cy.pop();
+                mark(coarse.dist ? "up" : "up (from the sub-cycle)", fine.N);
+                continue;
+            }
             const int fixed = step > 0 ? step : 0;
             const int n_pass = std::max(1, (fixed + 2) / 3), idx = next_scal();
             for (int k = 0; k < n_pass; ++k) {
@@ -1043,11 +1085,6 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
             }
             if (step > 0) {
                 deferred.push_back({record(1, fine.N, step, 0.0), idx});
-            } else if (step == -1) {
-                int done = 0;
-                double err_host = 0.0;
-                trigger_loop(lf, false, fine.N, done, err_host);
-                record(1, fine.N, done, err_host);
             } else if (step < -1) {              // :410-421: no sweep, the error is still evaluated
                 const int j = next_scal();
                 cy.pass(lf, L, 0, 0, true, j, 0, false, false, no_cb, no_fc, 0, no_uc, no_slab);

@@ -316,6 +316,29 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
                 continue;
             }
 
+            if (fused && step == -1) {
+                // error trigger (:194-240): two sweeps per launch with both errors; the launch that ends the loop has also
+                // restricted its residual, so the common two-sweep node is ONE launch and one synchronisation
+                cy.push(next_N);
+                l = &cy.stack_[cy.depth() - 2];
+                Level &c = cy.top();
+                int done = 0;
+                double err = 0.0;
+                double *resbuf = mgDownLegTrigger(fine_N, L, l->U, l->W, l->F, zero_init, next_N, c.F, &done, &err);
+                if (resbuf) {
+                    if (resbuf != l->U) std::swap(l->U, l->W);
+                    l->step = done;
+                    l->smoothing_error = err;
+                } else {                                              // a size the streaming kernel does not serve: one sweep per call
+                    if (zero_init) mgGridZero(l->N, l->U);
+                    done = cy.trigger_smooth(*l, L);
+                    mgDownLeg(fine_N, L, l->U, l->W, l->F, 0, 0, next_N, c.F, nullptr);
+                }
+                if (!quiet) { cy.log_smoothing(*l, done); fputs(kRestrictArt, stdout); }
+                cy.record(-1, fine_N, done, l->smoothing_error);
+                continue;
+            }
+
             if (zero_init) mgGridZero(l->N, l->U);
             int done;
             if (step == -1) done = cy.trigger_smooth(*l, L);
@@ -367,6 +390,22 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
                 continue;
             }
 
+            if (fused && step == -1) {
+                int done = 0;
+                double err = 0.0;
+                double *resbuf = mgUpLegTrigger(coarse.N, coarse.U, l->N, L, l->U, l->W, l->F, &done, &err);   // :350-408, two sweeps per launch
+                if (resbuf) {
+                    if (resbuf != l->U) std::swap(l->U, l->W);
+                    if (!quiet) fputs(kProlongArt, stdout);
+                    cy.pop();
+                    l = &cy.top();
+                    l->step = done;
+                    l->smoothing_error = err;
+                    cy.record(1, l->N, done, err);
+                    if (!quiet) cy.log_smoothing(*l, done);
+                    continue;
+                }
+            }
             if (fused) {
                 const int slot = step > 0 ? cy.next_slot() : -1;
                 double *resbuf = mgUpLeg(coarse.N, coarse.U, l->N, L, l->U, l->W, l->F, step > 0 ? step : 0,

@@ -4,6 +4,8 @@
 // mg_kernels.cu instead; both paths produce identical bits.
 #include "mg_fused.h"
 
+#include "../../include/mg_abi.h"
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -140,6 +142,9 @@ std::vector<int2> build_segments(int rows, int n_strips, int resident_warps, int
     return out;
 }
 
+// a pass over `rows` owned rows can be launched as edge segments + interior (build_segments: subset 1 / 2)
+bool segments_splittable(int rows) { return (rows + 23) / 24 >= 5; }
+
 const SegmentTable &segment_table(int rows, int n_strips, int resident_warps, int lead_rows, int subset)
 {
     static std::map<std::vector<int>, SegmentTable> cache;
@@ -189,7 +194,7 @@ int stream_launch_prepare(StreamParams &p, int W, int warps, int min_ctas, bool 
     if (p.Uout) p.Uout -= fine_shift;
     if (p.Fc) p.Fc -= (ptrdiff_t)p.fc_row0 * p.M;
     if (p.Uc) p.Uc -= (ptrdiff_t)p.uc_row0 * p.Nc;
-    if (err) p.partials = partials_buf((size_t)p.n_tasks);
+    if (err) p.partials = partials_buf(2 * (size_t)p.n_tasks);   // (MID passes keep a second partial per task)
     p.counter = c.counters + 8;   // [8] queue head, [9] finished warps (self-resetting)
     return std::max(1, std::min(min_ctas * c.sm_count, (p.n_tasks + warps - 1) / warps));
 }
@@ -234,6 +239,8 @@ bool tile_ok(const StreamParams &p)
            !p.raw_sum && !p.subset && !p.err_add;
 }
 
+bool tile_ok_size(int N) { return g_tile_max_N > 0 && N <= g_tile_max_N && (g_tile_even || N % 2 != 0); }
+
 template <int S, int IN, bool ERR, bool RES>
 void launch_tile(StreamParams &p)
 {
@@ -254,7 +261,7 @@ void launch_stream(StreamParams &p)
     if (tile_ok(p)) { launch_tile<S, IN, ERR, RES>(p); return; }
     // Measured on B200 (N = 16384): 4 columns per lane win for the passes without restriction (smoothing
     // pass 1.05 vs 1.09 ms); with restriction the 230-254 registers leave 8 warps per SM and lose (1.40 vs 1.22 ms).
-    if (IN != IN_PROLONG && !RES && g_cols4 && !(p.flag_lo || p.flag_hi)) {
+    if (IN != IN_PROLONG && !RES && g_cols4) {
         // instantiated only for IN_LOAD / IN_ZERO (the branch is dead for IN_PROLONG)
         constexpr int IN4 = IN == IN_PROLONG ? IN_LOAD : IN;
         using G4 = Stream4Geo<S, ERR || RES, RES>;
@@ -287,7 +294,7 @@ void launch_stream_any(int S, int in, int mode, StreamParams &p)
     // for passes WITHOUT restriction / prolongation on large grids (HBM bound: 0.93 of the measured peak against 0.87); the
     // -1 and 1 nodes are issue bound and need the 12-16 warps per SM only the 2-column kernel (k_stream) leaves room for.
     // Slab passes with peer memory: k_strip or k_stream (k_stream4 has no peer stores).
-    const bool peers = p.flag_lo || p.flag_hi;
+    const bool peers = p.peer_U_lo || p.peer_U_hi || p.peer_Fc_lo || p.peer_Fc_hi;
     const bool plain_pass = in != IN_PROLONG && mode != 2;
     if (g_strip && !tile_ok(p) && plain_pass && (p.N >= g_strip_min_N || peers)) { launch_strip(S, in, mode, p); return; }
     if (peers) { launch_stream_peer(S, in, mode, p); return; }
@@ -430,6 +437,37 @@ int restrict_first_coarse_at_or_after(int N, int M, int fine_row)
     return c;
 }
 
+// A slab pass with peer memory is launched in two parts: the thin row segments at both ends of the owned range -- they
+// produce every row a neighbour keeps as a halo, also of the restricted grid (8 coarse rows <= 22 fine rows up to ratio
+// 2.5) -- with the peer-store instantiation, then the interior with the plain kernel, which publishes the pass number
+// when it has drained.  The halo rows cross NVLink while the interior is swept, and the bulk of the pass runs the very
+// kernel of the single-GPU path (the peer-store variants cost 5-10 %: measured).  Slabs too thin to split: one launch.
+template <class Launch>
+void launch_slab(const StreamParams &base, const PeerLinks &peers, Launch launch)
+{
+    auto with_peers = [&](StreamParams &q) {
+        q.peer_U_lo = peers.U_lo; q.peer_U_hi = peers.U_hi; q.u_lo_end = peers.u_lo_end; q.u_hi_begin = peers.u_hi_begin;
+        q.peer_Fc_lo = peers.Fc_lo; q.peer_Fc_hi = peers.Fc_hi; q.fc_lo_end = peers.fc_lo_end; q.fc_hi_begin = peers.fc_hi_begin;
+    };
+    auto with_flags = [&](StreamParams &q) { q.flag_lo = peers.flag_lo; q.flag_hi = peers.flag_hi; q.flag_val = peers.flag_val; };
+    const bool stores = peers.U_lo || peers.U_hi || peers.Fc_lo || peers.Fc_hi;
+    if (stores && segments_splittable(base.own_hi - base.own_lo)) {
+        StreamParams a = base, b = base;
+        a.subset = 1;
+        with_peers(a);
+        launch(a);
+        b.subset = 2;
+        b.err_add = b.err_dev ? 1 : 0;           // the interior adds its error sum(s) to the edge launch's
+        with_flags(b);
+        launch(b);
+    } else {
+        StreamParams q = base;
+        with_peers(q);
+        with_flags(q);
+        launch(q);
+    }
+}
+
 void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
                bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
                const Slab *coarse_in, const PeerLinks &peers)
@@ -474,10 +512,151 @@ void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const dou
         p.c_dx = 1.0 / (double)(Nc - 1);
         p.inv_c_dx = 1.0 / p.c_dx;
     }
-    p.peer_U_lo = peers.U_lo; p.peer_U_hi = peers.U_hi; p.u_lo_end = peers.u_lo_end; p.u_hi_begin = peers.u_hi_begin;
-    p.peer_Fc_lo = peers.Fc_lo; p.peer_Fc_hi = peers.Fc_hi; p.fc_lo_end = peers.fc_lo_end; p.fc_hi_begin = peers.fc_hi_begin;
-    p.flag_lo = peers.flag_lo; p.flag_hi = peers.flag_hi; p.flag_val = peers.flag_val;
-    launch_stream_any(S, in_mode, mode, p);
+    launch_slab(p, peers, [&](StreamParams &q) { launch_stream_any(S, in_mode, mode, q); });
+}
+
+// ------------------------------------------------------------------ error-trigger loops (con_step = -1)
+namespace {
+
+// One pass of the trigger loop on a whole grid or a slab: S = 2 sweeps with BOTH errors (err[0] after the second, err[1]
+// after the first sweep), or S = 1 with err[0]; optional prolongation first (first pass of a 1 node), optional restriction.
+struct TriggerPass {
+    int N = 0, S = 2, in_mode = IN_LOAD;
+    double L = 1.0;
+    const double *in = nullptr, *F = nullptr;
+    double *out = nullptr;
+    int M = 0;                     // > 0: restrict into Fc
+    double *Fc = nullptr;
+    int Nc = 0;                    // IN_PROLONG
+    const double *Uc = nullptr;
+    double *err_dev = nullptr, *err_slot = nullptr;   // two consecutive doubles each
+    // row slab (rows == 0: the whole grid)
+    Slab fine, coarse_out, coarse_in;
+    bool slab = false;
+    PeerLinks peers;
+};
+
+void run_trigger_pass(const TriggerPass &t)
+{
+    const Spacing sp = spacing(t.N, t.L);
+    StreamParams p{};
+    p.N = t.N;
+    p.row0 = t.slab ? t.fine.row0 : 0;
+    p.rows = t.slab ? t.fine.rows : t.N;
+    p.own_lo = t.slab ? t.fine.own_lo : 0;
+    p.own_hi = t.slab ? t.fine.own_hi : t.N;
+    p.raw_sum = t.slab ? 1 : 0;
+    p.h2 = sp.h2;
+    p.inv_h2 = sp.inv_h2;
+    p.F = t.F;
+    p.Uin = t.in;
+    p.Uout = t.out;
+    p.err_dev = t.err_dev;
+    p.err_slot = t.err_slot;
+    if (t.M > 0) {
+        const FusedRestrictTable &rt = fused_restrict_table(t.N, t.M);
+        p.M = t.M;
+        p.Fc = t.Fc;
+        p.fc_row0 = t.slab ? t.coarse_out.row0 : 0;
+        p.f2c = rt.f2c;
+        p.rw = rt.rw;
+        p.rrow = rt.rrow;
+    }
+    if (t.in_mode == IN_PROLONG) {
+        const ProlongTable &pt = prolong_table(t.Nc, t.N);
+        p.Nc = t.Nc;
+        p.Uc = t.Uc;
+        p.uc_row0 = t.slab ? t.coarse_in.row0 : 0;
+        p.uc_rows = t.slab ? t.coarse_in.rows : t.Nc;
+        p.row_cell = pt.row_cell;
+        p.col_cell = pt.col_cell;
+        p.row_w = pt.row_w;
+        p.col_w = pt.col_w;
+        p.row_info = pt.row_info;
+        p.c_dx = 1.0 / (double)(t.Nc - 1);
+        p.inv_c_dx = 1.0 / p.c_dx;
+    }
+    launch_slab(p, t.peers, [&](StreamParams &q) {
+        if (t.S == 2) launch_stream_mid(t.in_mode, t.M > 0, q);
+        else launch_stream_any(t.S, t.in_mode, t.M > 0 ? 2 : 1, q);
+    });
+}
+
+constexpr double TRIGGER = 0.01;   // MG_solver_CPU.cpp:99
+
+// The loop of :216-230 / :388-402 -- sweep, error, stop when two successive errors differ by <= TRIGGER (at least two
+// sweeps) -- taken two sweeps per launch.  `first_mode` is the level 0 of the first pass (zero / load / prolong-add).  If the
+// loop ends after an odd number of sweeps the last launch went one sweep too far: it is repeated with one sweep from the
+// same input (passes are out of place, the input is still there).  With M > 0 every launch also restricts its result (the
+// last one is the one that counts), so a -1 node whose trigger fires at the minimum of two sweeps is ONE launch.
+double *trigger_loop(int N, double L, int first_mode, double *U, double *U_work, const double *F, int M, double *Fc, int Nc,
+                     const double *Uc, int *steps_out, double *error_out)
+{
+    Context &c = ctx();
+    double *slot = c.slots_host + (MG_SCALAR_SLOTS - 4), *slot_dev = c.slots_dev + (MG_SCALAR_SLOTS - 4);
+    double *cur = U, *other = U_work;
+    int done = 0, mode = first_mode;
+    double prev = 0.0, err = 0.0;
+    for (;;) {
+        TriggerPass t;
+        t.N = N; t.L = L; t.S = 2; t.in_mode = mode; t.in = cur; t.out = other; t.F = F; t.M = M; t.Fc = Fc; t.Nc = Nc; t.Uc = Uc;
+        t.err_dev = c.dev_scalar + 2;
+        t.err_slot = slot_dev;
+        run_trigger_pass(t);
+        check(cudaStreamSynchronize(c.stream), "cudaStreamSynchronize");
+        if (c.err_code) break;
+        const double e2 = slot[0], e1 = slot[1];
+        if (done + 1 > 1 && std::fabs(e1 - prev) <= TRIGGER) {        // the loop ends after the first of these two sweeps
+            t.S = 1;
+            run_trigger_pass(t);                                         // same input, one sweep (and its restriction)
+            check(cudaStreamSynchronize(c.stream), "cudaStreamSynchronize");
+            done += 1;
+            err = slot[0];
+            cur = other;
+            break;
+        }
+        done += 2;
+        cur = other;
+        other = (cur == U) ? U_work : U;
+        mode = IN_LOAD;
+        err = e2;
+        if (std::fabs(e2 - e1) <= TRIGGER) break;
+        prev = e2;
+    }
+    if (steps_out) *steps_out = done;
+    if (error_out) *error_out = err;
+    return cur;
+}
+
+}  // namespace
+
+bool trigger_fusable_down(int N, int M) { return streamable(N) && !tile_ok_size(N) && fused_restrict_table(N, M).usable; }
+bool trigger_fusable_up(int Nc, int N) { return streamable(N) && !tile_ok_size(N) && Nc >= 2 && (double)(N - 1) >= 1.2 * (double)(Nc - 1); }
+
+double *down_leg_trigger(int N, double L, double *U, double *U_work, const double *F, bool zero_init, int M, double *F_c, int *steps,
+                         double *error)
+{
+    return trigger_loop(N, L, zero_init ? IN_ZERO : IN_LOAD, U, U_work, F, M, F_c, 0, nullptr, steps, error);
+}
+
+double *up_leg_trigger(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, const double *F, int *steps, double *error)
+{
+    return trigger_loop(N, L, IN_PROLONG, U_f, U_work, F, 0, nullptr, Nc, U_c, steps, error);
+}
+
+void slab_trigger_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine, double *raw_err_dev2,
+                       int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc, const Slab *coarse_in, const PeerLinks &peers)
+{
+    TriggerPass t;
+    t.N = N; t.L = L; t.S = S; t.in_mode = in_mode; t.in = Uin; t.out = Uout; t.F = F;
+    t.M = coarse_out ? M : 0; t.Fc = Fc; t.Nc = Nc; t.Uc = Uc;
+    t.err_dev = raw_err_dev2;
+    t.slab = true;
+    t.fine = fine;
+    if (coarse_out) t.coarse_out = *coarse_out;
+    if (coarse_in) t.coarse_in = *coarse_in;
+    t.peers = peers;
+    run_trigger_pass(t);
 }
 
 void fused_init()

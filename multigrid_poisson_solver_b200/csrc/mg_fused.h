@@ -26,6 +26,14 @@ double *down_leg(int N, double L, double *U, double *U_work, const double *F, in
 double *up_leg(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, const double *F, int step,
                double *err_slot);
 
+// Error-trigger loops (con_step = -1, :194-240 / :376-408) two sweeps per launch; *steps = sweeps done, *error = the last
+// smoothing error (both valid on return: the loop synchronises once per launch).  Return the buffer holding the result.
+bool trigger_fusable_down(int N, int M);
+bool trigger_fusable_up(int Nc, int N);
+double *down_leg_trigger(int N, double L, double *U, double *U_work, const double *F, bool zero_init, int M, double *F_c, int *steps,
+                         double *error);
+double *up_leg_trigger(int Nc, const double *U_c, int N, double L, double *U_f, double *U_work, const double *F, int *steps, double *error);
+
 // ------------------------------------------------------------------ row slabs (multi-GPU, mg_dist.cu)
 // A slab holds global rows [row0, row0+rows) of an N-column grid and owns [own_lo, own_hi).
 struct Slab {
@@ -51,6 +59,9 @@ struct PeerLinks {
 void slab_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine,
                bool want_err, double *raw_err_dev, int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc,
                const Slab *coarse_in, const PeerLinks &peers);
+// one pass of a trigger loop on a slab: S = 2 (raw sums of both errors -> raw_err_dev2[0] last, [1] first sweep) or S = 1
+void slab_trigger_pass(int N, double L, int S, int in_mode, const double *Uin, const double *F, double *Uout, const Slab &fine, double *raw_err_dev2,
+                       int M, double *Fc, const Slab *coarse_out, int Nc, const double *Uc, const Slab *coarse_in, const PeerLinks &peers);
 void dist_release_on_shutdown();   // mgShutdown: the slab driver's arenas and cached source go with the context
 
 // Row segments {first, past-last} (relative to the first owned row) a fused pass over `rows` owned rows
@@ -66,5 +77,8 @@ int stream_launch_prepare(StreamParams &p, int W, int warps, int min_ctas, bool 
 void launch_strip(int S, int in, int mode, StreamParams &p);
 // the -1 node (in 0 / 1, mode 2) or the 1 node (in 2, mode 0 / 1) on a slab with peer memory (mg_peer.cu)
 void launch_stream_peer(int S, int in, int mode, StreamParams &p);
+// two sweeps with both smoothing errors (error-trigger loops); in: 0 load, 1 zero (res only), 2 prolong (no res); peer stores
+// when the parameters carry flag words (mg_peer.cu)
+void launch_stream_mid(int in, bool res, StreamParams &p);
 
 }  // namespace mg

@@ -37,7 +37,39 @@ void launch_s(int S, StreamParams &p)
     }
 }
 
+template <int IN, bool RES, bool PEER>
+void launch_mid(StreamParams &p)
+{
+    using G = StreamGeo<2, true, RES>;
+    constexpr int warps = stream_shape(RES).warps, ctas = stream_shape(RES).min_ctas, smem = stream_smem_bytes(IN, warps);
+    const int blocks = stream_launch_prepare(p, G::W, warps, ctas, true, 2 * 2 + 3);
+    if (blocks == 0) return;
+    static bool opted_in = false;
+    if (!opted_in) {
+        check(cudaFuncSetAttribute(k_stream<2, IN, true, RES, PEER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute(k_stream, mid)");
+        opted_in = true;
+    }
+    Context &c = ctx();
+    k_stream<2, IN, true, RES, PEER, true><<<blocks, warps * 32, smem, c.stream>>>(p);
+    c.launches++;
+    check(cudaGetLastError(), "k_stream (mid)");
+}
+
+template <bool PEER>
+void launch_mid_any(int in, bool res, StreamParams &p)
+{
+    if (in == IN_PROLONG) launch_mid<IN_PROLONG, false, PEER>(p);
+    else if (res) { if (in == IN_ZERO) launch_mid<IN_ZERO, true, PEER>(p); else launch_mid<IN_LOAD, true, PEER>(p); }
+    else { if (in == IN_ZERO) launch_mid<IN_ZERO, false, PEER>(p); else launch_mid<IN_LOAD, false, PEER>(p); }
+}
+
 }  // namespace
+
+void launch_stream_mid(int in, bool res, StreamParams &p)
+{
+    if (p.peer_U_lo || p.peer_U_hi || p.peer_Fc_lo || p.peer_Fc_hi) launch_mid_any<true>(in, res, p);
+    else launch_mid_any<false>(in, res, p);
+}
 
 // in: 0 load, 1 zero, 2 prolong; mode: 2 (ERR + RES) for in 0 / 1, 0 or 1 for in 2
 void launch_stream_peer(int S, int in, int mode, StreamParams &p)

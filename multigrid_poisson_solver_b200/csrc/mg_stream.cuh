@@ -176,7 +176,7 @@ __device__ __forceinline__ bool div2_unsafe(double x)
 // warps in order: the summation tree depends only on the task geometry and the CTA shape, never on
 // which warp ran which task.  A whole CTA keeps 16 loads per thread in flight (a lone warp needed
 // ~1 us per 1024 partials: 14-20 us of tail at N >= 8192).
-template <int WARPS, bool ERR>
+template <int WARPS, bool ERR, bool MID = false>
 __device__ __forceinline__ void finish_launch(const StreamParams &p)
 {
     __shared__ double fold_s[WARPS];
@@ -197,31 +197,37 @@ __device__ __forceinline__ void finish_launch(const StreamParams &p)
         if (p.flag_hi) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_hi), "r"(p.flag_val) : "memory");
     }
     if (ERR) {
-        double s = 0.0;
-        for (int k0 = tid; k0 < p.n_tasks; k0 += T * 16) {
-            double v[16];
+        // which: 0 the error after the last sweep -> err[0]; 1 (MID) the error after the first of two sweeps -> err[1]
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = k0 + T * j < p.n_tasks ? __ldcg(&p.partials[k0 + T * j]) : 0.0;
+        for (int which = 0; which < (MID ? 2 : 1); ++which) {
+            const double *part = p.partials + (size_t)which * p.n_tasks;
+            double s = 0.0;
+            for (int k0 = tid; k0 < p.n_tasks; k0 += T * 16) {
+                double v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s = __dadd_rn(s, v[j]);
-        }
+                for (int j = 0; j < 16; ++j) v[j] = k0 + T * j < p.n_tasks ? __ldcg(&part[k0 + T * j]) : 0.0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-        if (lane == 0) fold_s[warp] = s;
-        __syncthreads();
-        if (tid == 0) {
-            s = fold_s[0];
-#pragma unroll
-            for (int w = 1; w < WARPS; ++w) s = __dadd_rn(s, fold_s[w]);
-            double e = s;
-            if (p.err_add && p.err_dev) e = __dadd_rn(*p.err_dev, s);   // second launch of a split pass
-            if (!p.raw_sum) {
-                e = __dadd_rn(s, s);                              // sum1 + sum2 over the same parity (:621)
-                e = __ddiv_rn(e, (double)p.N);
-                e = __ddiv_rn(e, (double)p.N);
+                for (int j = 0; j < 16; ++j) s = __dadd_rn(s, v[j]);
             }
-            if (p.err_dev) *p.err_dev = e;
-            if (p.err_slot) *p.err_slot = e;                      // host-mapped; the host reads it after a stream sync
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (which) __syncthreads();           // fold_s is reused
+            if (lane == 0) fold_s[warp] = s;
+            __syncthreads();
+            if (tid == 0) {
+                s = fold_s[0];
+#pragma unroll
+                for (int w = 1; w < WARPS; ++w) s = __dadd_rn(s, fold_s[w]);
+                double e = s;
+                if (p.err_add && p.err_dev) e = __dadd_rn(p.err_dev[which], s);   // second launch of a split pass
+                if (!p.raw_sum) {
+                    e = __dadd_rn(s, s);                          // sum1 + sum2 over the same parity (:621)
+                    e = __ddiv_rn(e, (double)p.N);
+                    e = __ddiv_rn(e, (double)p.N);
+                }
+                if (p.err_dev) p.err_dev[which] = e;
+                if (p.err_slot) p.err_slot[which] = e;            // host-mapped; the host reads it after a stream sync
+            }
         }
     }
     if (tid == 0) {
@@ -300,9 +306,12 @@ struct BoolTag { static constexpr bool value = B; };
 
 // PEER: row slabs with peer memory -- the rows a neighbouring GPU keeps as its halo are also stored straight into its
 // array (a separate instantiation, mg_peer.cu: the single-GPU kernels sit exactly at their register limits).
-template <int S, int IN, bool ERR, bool RES, bool PEER = false>
+// MID (S == 2 only): also the smoothing error after the FIRST of the two sweeps (partials [n_tasks, 2 n_tasks), result in
+// err[1]) -- the error-trigger loop (:216-230) takes two sweeps per launch and still sees every sweep's error.
+template <int S, int IN, bool ERR, bool RES, bool PEER = false, bool MID = false>
 __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES).min_ctas) k_stream(const StreamParams p)
 {
+    static_assert(!MID || (S == 2 && ERR), "MID: two sweeps with both errors");
     constexpr int STREAM_WARPS = stream_shape(RES).warps;
     constexpr bool NEED_R = ERR || RES;
     using G = StreamGeo<S, NEED_R, RES>;
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         ox = col_ok ? (unsigned)(cqx - cbase) * 8u : 0u;     // lanes outside the grid read slot element 0 (unused)
         oy = col_ok ? (unsigned)(cqy - cbase) * 8u : 0u;
     }
-    double err_acc = 0.0;
+    double err_acc = 0.0, mid_acc = 0.0;
 
     auto cell_of_row = [&](int r) {              // row_cell[min(r, N-1)] for the row being issued (non-decreasing r)
         if (r - tab_base >= 32) {
@@ -579,12 +588,23 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 } else {
                     const double2 below = w[t][k & 1], c = w[t][(k & 1) ^ 1];
                     const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
-                    nx.x = jacobi_fast(c.x, sum4(x.x, below.x, c.y, left), __dmul_rn(h2, f.x));
-                    nx.y = jacobi_fast(c.y, sum4(x.y, below.y, right, c.x), __dmul_rn(h2, f.y));
+                    const double s4x = sum4(x.x, below.x, c.y, left), s4y = sum4(x.y, below.y, right, c.x);
+                    nx.x = jacobi_fast(c.x, s4x, __dmul_rn(h2, f.x));
+                    nx.y = jacobi_fast(c.y, s4y, __dmul_rn(h2, f.y));
                     if (!FAST) {                                  // boundary rows / columns are carried over
                         const bool row_in = i > 0 && i < N - 1;
                         nx.x = (row_in && x_in) ? nx.x : c.x;
                         nx.y = (row_in && y_in) ? nx.y : c.y;
+                    }
+                    if (MID && t == 1) {
+                        // the smoothing error of level 1 (after the first sweep): its row i is the centre of this very stencil
+                        double v = (i & 1) ? residual_fast(c.y, s4y, f.y, inv_h2) : residual_fast(c.x, s4x, f.x, inv_h2);   // red point (:609-611)
+                        if (!FAST) {
+                            const bool row_in = i > 0 && i < N - 1;
+                            v = (row_in && ((i & 1) ? y_in : x_in)) ? v : 0.0;
+                        }
+                        const bool take = col_own && i >= own_r_lo && i < own_r_hi;
+                        mid_acc = __dadd_rn(mid_acc, take ? fabs(v) : 0.0);
                     }
                     w[t][k & 1] = x;
                 }
@@ -677,6 +697,12 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
         if (lane == 0) p.partials[task] = v;
+        if (MID) {
+            double m = mid_acc;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) m = __dadd_rn(m, __shfl_down_sync(0xffffffffu, m, off));
+            if (lane == 0) p.partials[p.n_tasks + task] = m;
+        }
     }
     if (p.trace && lane == 0) {
         unsigned long long t1;
@@ -690,7 +716,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     }
   }  // task loop
 
-    finish_launch<STREAM_WARPS, ERR>(p);
+    finish_launch<STREAM_WARPS, ERR, MID>(p);
 }
 
 }  // namespace mg
