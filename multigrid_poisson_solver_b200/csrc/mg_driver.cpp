@@ -270,7 +270,33 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
     auto have = [&](size_t n) { return cur + n <= tok.size(); };
     auto next_int = [&]() { return (int)tok[cur++]; };
     const int tail_max_N = (fused && !dry && !getenv("MG_NO_TAIL")) ? mgCoarseTailMaxN() : 0;
+    // MG_TRACE=1: per-node time line of the cycle on stderr (device time between the nodes' last launches)
+    struct Mark { int node, N; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    static const bool tracing = getenv("MG_TRACE") && atoi(getenv("MG_TRACE")) != 0;
+    auto mark = [&](int node_, int N_) {
+        if (!tracing || dry) return;
+        Mark m{node_, N_, nullptr};
+        cudaEventCreate(&m.ev);
+        cudaEventRecord(m.ev, (cudaStream_t)mgStream());
+        marks.push_back(m);
+    };
+    struct MarkDump {
+        std::vector<Mark> &m;
+        ~MarkDump()
+        {
+            if (m.size() > 1) cudaEventSynchronize(m.back().ev);
+            for (size_t i = 1; i < m.size(); ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, m[i - 1].ev, m[i].ev);
+                fprintf(stderr, "[mg trace] node %2d N=%-6d device %8.3f ms\n", m[i].node, m[i].N, ms);
+            }
+            for (Mark &k : m) cudaEventDestroy(k.ev);
+        }
+    } mark_dump{marks};
+    mark(9, cy.top().N);
     while (have(1)) {                                                 // :158-160 (stops at EOF instead of re-running)
+        if (tracing && !marks.empty() && !cy.stack_.empty()) mark(node, cy.top().N);
         // ---- coarse tail: the whole sub-cycle below a small level in one kernel (mg_tail.cu)
         if (tail_max_N && cy.top().N <= tail_max_N && ((int)tok[cur] == -1 || (int)tok[cur] == 0)) {
             const int took = cy.try_tail(tok, cur, pos, ladder, con_step, con_N, L, quiet);

@@ -170,6 +170,7 @@ bool g_tile_even = false;
 int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
 int g_strip = 1;   // the bulk-copy 4-column kernel (mg_strip.cuh, instantiated in mg_legs.cu) for smoothing passes; MG_STRIP=0: never
 int g_strip_min_N = 8192;   // ... from this grid size on (MG_STRIP_MIN_N)
+long long g_split_min_points = 32ll << 20;   // slab passes are split into edge + interior launches from this many owned points on (MG_SPLIT_MIN_POINTS)
 
 // Task geometry and persistent grid shared by the streaming kernels: fills the task fields of `p`, shifts the array
 // bases to global rows and returns the CTA count (0: nothing to launch).
@@ -451,7 +452,8 @@ void launch_slab(const StreamParams &base, const PeerLinks &peers, Launch launch
     };
     auto with_flags = [&](StreamParams &q) { q.flag_lo = peers.flag_lo; q.flag_hi = peers.flag_hi; q.flag_val = peers.flag_val; };
     const bool stores = peers.U_lo || peers.U_hi || peers.Fc_lo || peers.Fc_hi;
-    if (stores && segments_splittable(base.own_hi - base.own_lo)) {
+    // (small slabs are latency bound: a second launch costs more than the peer-store variant does)
+    if (stores && segments_splittable(base.own_hi - base.own_lo) && (long long)(base.own_hi - base.own_lo) * base.N >= g_split_min_points) {
         StreamParams a = base, b = base;
         a.subset = 1;
         with_peers(a);
@@ -669,6 +671,7 @@ void fused_init()
     if (const char *d = getenv("MG_COLS4")) g_cols4 = atoi(d);
     if (const char *d = getenv("MG_STRIP")) g_strip = atoi(d);
     if (const char *d = getenv("MG_STRIP_MIN_N")) g_strip_min_N = atoi(d);
+    if (const char *d = getenv("MG_SPLIT_MIN_POINTS")) g_split_min_points = atoll(d);
     if (const char *d = getenv("MG_TILE_MAX_N")) { g_tile_max_N = std::max(0, atoi(d)); g_tile_even = true; }
 }
 
