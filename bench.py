@@ -479,6 +479,26 @@ def main():
     return 0
 
 
+def topology(local):
+    """Where this rank's GPU hangs and which CPUs the process may use (NUMA placement of the pinned buffers)."""
+    out = {"cpus_allowed": len(os.sched_getaffinity(0))}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        out["gpu_pci"] = bdf
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            out["gpu_numa_node"] = int(f.read())
+    except Exception:
+        pass
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        out["numa_nodes"] = len(nodes)
+    except Exception:
+        pass
+    return out
+
+
 WEAK_N = {1: 16384, 2: 23168, 4: 32768, 8: 46336}   # N^2 per GPU constant (16384^2), even ladders down to the threshold
 
 
@@ -563,8 +583,32 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
         barrier()
         wall = time.perf_counter() - t0
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1000.0 * wall)) / e2e_steps
+        # the host-side ceiling of that call: the same two copies per rank and step (pinned -> device, device -> pinned),
+        # all ranks at once, nothing else -- what the PCIe links and the host memory of this box give 'world' GPUs together
+        dF = torch.empty_like(hF[0], device="cuda")
+        dU = torch.empty_like(hU[0], device="cuda")
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        def copies(k):
+            for i in range(k):
+                with torch.cuda.stream(s_up):
+                    dF.copy_(hF[i % 2], non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    hU[i % 2].copy_(dU, non_blocking=True)
+            s_up.synchronize(); s_dn.synchronize()
+        copies(1)
+        barrier()
+        t0 = time.perf_counter()
+        copies(4)
+        barrier()
+        ceil_ms = max_over_ranks(1000.0 * (time.perf_counter() - t0)) / 4
+        del dF, dU
         e2e = {"value": (n / base_n) * 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": 8 * rows.value * N,
                "d2h_bytes_per_step": 8 * (ohi.value - olo.value) * N, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "host_ceiling": {"ms_per_step": ceil_ms, "value": (n / base_n) * 1000.0 / ceil_ms,
+                                "aggregate_GBs_each_way": world * 8 * rows.value * N / (ceil_ms * 1e6),
+                                "what": "the step's two copies alone (no compute), all ranks at once, full duplex: the most this box's PCIe links "
+                                        "and host memory allow; e2e / this = how much of the copy time the cycles are hidden behind",
+                                "topology": topology(local)},
                "call": "mgDistRunCycleFileHostBatch on every rank (one problem per step: pinned source slab -> device, V-cycle on the "
                        "slabs, owned rows of U -> pinned host; upload of step i+1 and download of step i-1 overlap the cycle of step i); "
                        "bytes are per rank"}
