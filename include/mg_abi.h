@@ -79,6 +79,8 @@ void doExactSolver(int N, double L, double *U, double *F, double target_error, i
 void getAnalytic(int N, double L, double *U, double min_x, double min_y);
 /* mean |analytic - U| of the final report, MG_solver_CPU.cpp:434-445 (synchronous) */
 double mgAnalyticError(int N, double L, const double *U, double min_x, double min_y);
+/* mean |A - B| over N^2 points (the final report's reduction with a caller-supplied reference grid; synchronous) */
+double mgMeanAbsDiff(int N, const double *A, const double *B);
 /* Gauss-Seidel iterations taken by the last doExactSolver(option 1) (synchronous) */
 int mgLastExactSolverIterations(void);
 
@@ -170,6 +172,24 @@ typedef struct mgCycleResult {
  * final solution.  Returns 0 on success. */
 int mgRunCycleFile(const char *path, int flags, const double *F_top, double *U_top,
                    mgTraceRec *recs, int max_recs, mgCycleResult *res);
+
+/* The problem plug point (the reference compiles the problem in: source MG_solver_CPU.cpp:488, boundary :509-519,
+ * analytic solution :544).  Any member may be NULL (= the reference's built-in).  All grids are device arrays of N_max^2.
+ *   F_top         the source grid (used in place, never written)
+ *   U0_top        an initial grid INCLUDING its boundary values: non-zero Dirichlet data.  The top level then starts the
+ *                 way the reference restarts (:209-211): its first -1 node keeps U instead of zeroing it; sweeps touch
+ *                 interior points only (:587-599), so the boundary data are carried and enter every residual.
+ *   analytic_top  the reference solution of the final error report (:434-445) */
+typedef struct mgProblem {
+    const double *F_top;
+    const double *U0_top;
+    const double *analytic_top;
+} mgProblem;
+int mgRunCycleFileEx(const char *path, int flags, const mgProblem *prob, double *U_top, mgTraceRec *recs, int max_recs,
+                     mgCycleResult *res);
+/* the same with HOST grids (each may be NULL) */
+int mgRunCycleFileHostEx(const char *path, int flags, const double *F_host, const double *U0_host, const double *analytic_host,
+                         double *U_host, mgTraceRec *recs, int max_recs, mgCycleResult *res);
 
 /* The same interpreter on ONE level owned by the caller: runs the node sub-stream that starts at
  * tok[*cur] (tok = the cycle file as numeric tokens) and returns to that level; stops before the

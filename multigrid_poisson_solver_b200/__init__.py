@@ -9,6 +9,6 @@ There is no CPU fallback: importing works anywhere, but every operator needs the
 library and a CUDA device and raises loudly otherwise.
 """
 from .api import (run_cycle_dist_emulated, run_cycle_dist, dist_init, dist_plan,  # noqa: F401
-                  MGLibraryError, DeviceGrid, GpuOps, init, lib, lib_path, run_cycle, run_cycle_host, run_cycle_host_batch,  # noqa: F401
+                  MGLibraryError, DeviceGrid, GpuOps, init, lib, lib_path, run_cycle, run_cycle_host, run_cycle_host_batch, run_cycle_problem,  # noqa: F401
                   RUN_FUSED, RUN_UNFUSED, RUN_QUIET, RUN_SKIP_SOURCE, RUN_NO_FINAL_ERROR)
 from . import cycles  # noqa: F401

@@ -66,6 +66,9 @@ ABI = {
     "mgCoarseTailMaxOps": (C.c_int, []),
     "mgCoarseTail": (C.c_int, [C.c_double, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp]),
     "mgRunCycleFile": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
+    "mgMeanAbsDiff": (C.c_double, [C.c_int, _vp, _vp]),
+    "mgRunCycleFileEx": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
+    "mgRunCycleFileHostEx": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(TraceRec), C.c_int, C.POINTER(CycleResult)]),
     "mgRunSubcycle": (C.c_int, [_dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                 C.c_double, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, C.c_int, C.POINTER(C.c_int), C.c_int,
                                 C.POINTER(TraceRec), C.c_int, C.POINTER(C.c_int), C.c_int]),
@@ -304,6 +307,34 @@ def run_cycle_host(path, flags=RUN_FUSED | RUN_QUIET, F_host=None, want_U=True, 
         assert F_host.size == N * N
         Fp = F_host.ctypes.data
     return _run("mgRunCycleFileHost", path, flags, Fp, N if want_U else 0, max_recs)
+
+
+def run_cycle_problem(path, flags=RUN_FUSED | RUN_QUIET, F_host=None, U0_host=None, analytic_host=None, max_recs=8192):
+    """mgRunCycleFileHostEx: the problem plug point -- caller-supplied source, initial grid with (non-zero) Dirichlet boundary
+    data, and reference solution of the final error report."""
+    l = _need()
+    N = _n_max(path)
+    keep = []
+
+    def ptr(a):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        assert a.size == N * N
+        keep.append(a)
+        return a.ctypes.data
+
+    recs = (TraceRec * max_recs)()
+    res = CycleResult()
+    U = np.empty(N * N)
+    rc = l.mgRunCycleFileHostEx(os.fsencode(path), flags, ptr(F_host), ptr(U0_host), ptr(analytic_host), U.ctypes.data, recs, max_recs,
+                                C.byref(res))
+    if rc != 0:
+        msg = l.mgLastError().decode()
+        l.mgClearError()
+        raise MGLibraryError("mgRunCycleFileHostEx(%s) failed with code %d %s" % (path, rc, msg))
+    trace = [dict(node=r.node, N=r.N, steps=r.steps, err=r.err) for r in recs[:res.n_recs]]
+    return dict(trace=trace, U=U, N=res.N, mg_error=res.mg_error, time_ms=res.time_ms, launches=res.launches)
 
 
 def run_cycle_host_batch(path, F_hosts, flags=RUN_FUSED | RUN_QUIET, U_ptrs=None):

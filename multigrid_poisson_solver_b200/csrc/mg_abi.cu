@@ -338,6 +338,17 @@ double mgAnalyticError(int N, double L, const double *U, double min_x, double mi
     return out;
 }
 
+double mgMeanAbsDiff(int N, const double *A, const double *B)
+{
+    if (!ensure_ready()) return -1.0;
+    Context &c = ctx();
+    launch_mean_abs_diff((size_t)N * N, A, B, (double)N * (double)N, c.dev_scalar + 1);
+    double out = -1.0;
+    check(cudaMemcpyAsync(&out, c.dev_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+    check(cudaStreamSynchronize(c.stream), "cudaStreamSynchronize");
+    return out;
+}
+
 // ------------------------------------------------------------------ fused operators
 void mgSmooth(int N, double L, const double *U_in, double *F, int step, double *U_out, double *error_slot)
 {

@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -1025,6 +1026,15 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
         node = next_int();
         if (node == 2) break;
         if (c.err_code) { rc = 10; break; }
+        struct NodeRange {                       // one NVTX range per distributed node (a no-op without a profiler)
+            NodeRange(int node_, int N_)
+            {
+                char label[56];
+                snprintf(label, sizeof label, "slab node %d N=%d", node_, N_);
+                nvtxRangePushA(label);
+            }
+            ~NodeRange() { nvtxRangePop(); }
+        } nvtx_range(node, cy.geom.back().N);
         if (node == -1) {
             int step, next_N;
             if (con_step == 0) { if (!have(1)) { rc = 3; break; } step = next_int(); } else step = con_step;

@@ -8,6 +8,7 @@
 //   MG_RUN_UNFUSED  one ABI operator per reference call (literal drop-in)
 //   MG_RUN_FUSED    mgDownLeg / mgUpLeg per node, no D / tempU grids, no host sync per node
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <chrono>
 #include <cmath>
@@ -23,6 +24,17 @@
 namespace {
 
 constexpr double TRIGGER = 0.01;  // MG_solver_CPU.cpp:99
+
+// One NVTX range per node of the cycle ("node -1 N=16384"): shows up in nsys / ncu time lines; a no-op without a profiler.
+struct NodeRange {
+    NodeRange(int node, int N)
+    {
+        char label[48];
+        snprintf(label, sizeof label, "node %d N=%d", node, N);
+        nvtxRangePushA(label);
+    }
+    ~NodeRange() { nvtxRangePop(); }
+};
 
 struct Level {
     int N = 0;
@@ -308,6 +320,7 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
         node = next_int();
         if (node == 2) break;                                         // :162
         if (mgLastErrorCode()) { rc = 10; break; }
+        const NodeRange nvtx_range(node, cy.stack_.empty() ? 0 : cy.top().N);
 
         if (node == -1) {                                             // :169-301
             int step, next_N;
@@ -476,8 +489,12 @@ int interpret(Cycle &cy, NodeStream &s, size_t stop_depth)
     return rc;
 }
 
+// U0_top / analytic_top: the problem plug point.  U0_top (device, N_max^2) is an initial grid INCLUDING its
+// boundary values -- non-zero Dirichlet data; the cycle then starts the way the reference restarts (:209-211): the first -1
+// node of the top level keeps U instead of zeroing it, the boundary is carried through every sweep (:587-599 touch interior
+// points only) and enters the residual.  analytic_top replaces getAnalytic in the final report (:434-445).
 int run(const char *path, int flags, const double *F_top, double *U_top, mgTraceRec *recs, int max_recs,
-        mgCycleResult *res)
+        mgCycleResult *res, const double *U0_top = nullptr, const double *analytic_top = nullptr)
 {
     std::ifstream f(path);
     if (!f.is_open()) {
@@ -512,6 +529,10 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
         cy.push(N_max);                                               // :149
         getSource(N_max, L, cy.top().F, min_x, min_y);                // :153 (outside the timer)
     }
+    if (U0_top) {
+        mgGridCopy(N_max, cy.top().U, U0_top);
+        cy.init_ = 0;                                                 // "more like a restart method" (:210)
+    }
     mgSync();
 
     cudaStream_t stream = (cudaStream_t)mgStream();
@@ -544,7 +565,8 @@ int run(const char *path, int flags, const double *F_top, double *U_top, mgTrace
 
     if (rc == 0 && !cy.stack_.empty()) {
         Level &l = cy.top();
-        if (res && !(flags & MG_RUN_NO_FINAL_ERROR)) res->mg_error = mgAnalyticError(l.N, L, l.U, min_x, min_y);   // :434-445
+        if (res && !(flags & MG_RUN_NO_FINAL_ERROR))                  // :434-445
+            res->mg_error = analytic_top ? mgMeanAbsDiff(l.N, analytic_top, l.U) : mgAnalyticError(l.N, L, l.U, min_x, min_y);
         if (U_top) { mgGridCopy(l.N, U_top, l.U); mgSync(); }
         if (!quiet && res) {
             printf("\n\n");
@@ -624,6 +646,37 @@ extern "C" int mgRunCycleFile(const char *path, int flags, const double *F_top, 
 {
     if (mgLastErrorCode()) return 10;
     return run(path, flags, F_top, U_top, recs, max_recs, res);
+}
+
+extern "C" int mgRunCycleFileEx(const char *path, int flags, const mgProblem *prob, double *U_top, mgTraceRec *recs, int max_recs,
+                                mgCycleResult *res)
+{
+    if (mgLastErrorCode()) return 10;
+    if (!prob) return run(path, flags, nullptr, U_top, recs, max_recs, res);
+    if (prob->F_top) flags |= MG_RUN_SKIP_SOURCE;
+    return run(path, flags, prob->F_top, U_top, recs, max_recs, res, prob->U0_top, prob->analytic_top);
+}
+
+extern "C" int mgRunCycleFileHostEx(const char *path, int flags, const double *F_host, const double *U0_host, const double *analytic_host,
+                                    double *U_host, mgTraceRec *recs, int max_recs, mgCycleResult *res)
+{
+    if (mgLastErrorCode()) return 10;
+    std::ifstream f(path);
+    if (!f.is_open()) { fprintf(stderr, "[ ERROR ]: Cannot open file %s\n", path); return 1; }
+    double L, mx, my; int cs, cn, N_max, N_min;
+    f >> L >> mx >> my >> cs >> cn >> N_max >> N_min;
+    if (!f) return 2;
+    f.close();
+    double *dF = nullptr, *dU0 = nullptr, *dA = nullptr, *dU = nullptr;
+    if (F_host) { dF = mgGridAlloc(N_max); mgGridUpload(N_max, dF, F_host); }
+    if (U0_host) { dU0 = mgGridAlloc(N_max); mgGridUpload(N_max, dU0, U0_host); }
+    if (analytic_host) { dA = mgGridAlloc(N_max); mgGridUpload(N_max, dA, analytic_host); }
+    if (U_host) dU = mgGridAlloc(N_max);
+    mgProblem prob{dF, dU0, dA};
+    const int rc = mgRunCycleFileEx(path, flags, &prob, dU, recs, max_recs, res);
+    if (rc == 0 && U_host) mgGridDownload(N_max, dU, U_host);
+    mgGridFree(dF); mgGridFree(dU0); mgGridFree(dA); mgGridFree(dU);
+    return rc;
 }
 
 extern "C" int mgRunCycleFileHost(const char *path, int flags, const double *F_host, double *U_host, mgTraceRec *recs,

@@ -322,6 +322,36 @@ def test_cli_log_matches_reference_binary(golden_dir, tmp_path):
         assert open(tmp_path / ("Sol_GPU_cycle_%s.txt" % name)).read() == open(os.path.join(golden_dir, "MG_CPU_%s.csv" % name)).read()
 
 
+def test_problem_plug_point_nonzero_dirichlet(orc, tmp_path):
+    """caller-supplied source, initial grid carrying NON-ZERO Dirichlet boundary values, and reference
+    solution.  Checked against the same node sequence composed from the oracle's operators (the reference compiles
+    its problem in, :488 / :509-519 / :544, so its main() cannot run this): U bit-identical, errors <= 1e-10."""
+    import multigrid_poisson_solver_b200 as mg
+    N, M = 64, 32
+    rng = np.random.default_rng(9)
+    x = np.linspace(0.0, 1.0, N)
+    exact = np.add.outer(np.sin(2.0 * x), np.cos(3.0 * x))          # u(x, y); Laplace(u) = -(4 sin 2y' ... ) supplied as F below
+    F = -(4.0 * np.sin(2.0 * x)[:, None] + 9.0 * np.cos(3.0 * x)[None, :]) + 0.0 * exact
+    U0 = np.zeros((N, N))
+    U0[0, :], U0[-1, :], U0[:, 0], U0[:, -1] = exact[0, :], exact[-1, :], exact[:, 0], exact[:, -1]   # Dirichlet data, zero interior
+    F, U0, exact = F.reshape(-1), U0.reshape(-1), exact.reshape(-1)
+    path = tmp_path / "two_grid.txt"
+    path.write_text(mg.cycles.two_grid(N, M, step=3, tol=1e-6))
+    for flags in (mg.RUN_FUSED | mg.RUN_QUIET, mg.RUN_UNFUSED | mg.RUN_QUIET):
+        r = mg.run_cycle_problem(str(path), flags, F_host=F, U0_host=U0, analytic_host=exact)
+        # the same nodes with the oracle's operators: -1 (U kept: restart semantics), 0, 1
+        U, e_down = orc.doSmoothing(N, 1.0, U0, F, 3)
+        Fc = orc.doRestriction(N, -orc.getResidual(N, 1.0, U, F), M)
+        Uc = orc.doExactSolver(M, 1.0, Fc, 1e-6, 1)
+        U = orc.doGridAddition(N, U, orc.doProlongation(M, Uc, N))
+        U, e_up = orc.doSmoothing(N, 1.0, U, F, 3)
+        assert_same(r["U"], U, "plug point U")
+        errs = [t["err"] for t in r["trace"] if t["node"] != 0]
+        assert errs[0] == pytest.approx(e_down, rel=ERR_RTOL) and errs[1] == pytest.approx(e_up, rel=ERR_RTOL)
+        assert r["mg_error"] == pytest.approx(np.mean(np.abs(exact - U)), rel=1e-12)
+        assert np.array_equal(r["U"].reshape(N, N)[0], exact.reshape(N, N)[0])      # the boundary data came through untouched
+
+
 # ------------------------------------------------------------------ full-size properties (no oracle needed)
 @pytest.mark.parametrize("N", [4096, 16384])
 def test_full_size_properties(N):
