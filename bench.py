@@ -506,9 +506,11 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
     """Weak scaling of the row-slab driver: the grid grows with the GPU count so that every GPU keeps
     16384^2 fine points; one process per GPU, halo rows by peer stores of the fused kernels, levels < 1024 rows redundant on every rank."""
     threshold = int(os.environ.get("MG_DIST_THRESHOLD", "1024"))
-    N = args.nmax if args.nmax else WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256)
+    wl = workloads()[args.config]
+    weak = args.config == "v16384" and not args.nmax     # the headline: weak scaling; any other workload: the same grid on more GPUs
+    N = args.nmax if args.nmax else (WEAK_N.get(world, int(round(16384 * world ** 0.5 / 256)) * 256) if weak else wl["N"])
     n = N * N
-    base_n = 16384 * 16384
+    base_n = 16384 * 16384 if weak else n
 
     def bcast(b):
         obj = [b]
@@ -516,15 +518,16 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
         return obj[0]
 
     mg.dist_init(rank, world, bcast)
-    path = write_cycle(cycles.v_cycle(N, 8))
+    path = write_cycle(wl["text"](N))
     flags = mg.RUN_FUSED | mg.RUN_QUIET | mg.RUN_NO_FINAL_ERROR | mg.RUN_SKIP_SOURCE
-    recs = (api.TraceRec * 64)()
+    max_recs = 8192
+    recs = (api.TraceRec * max_recs)()
     res = api.CycleResult()
     import ctypes as C
     lo, hi = C.c_int(0), C.c_int(0)
 
     def one_cycle(u_host=None):
-        rc = lib.mgDistRunCycleFile(os.fsencode(path), threshold, flags, u_host, C.byref(lo), C.byref(hi), recs, 64, res)
+        rc = lib.mgDistRunCycleFile(os.fsencode(path), threshold, flags, u_host, C.byref(lo), C.byref(hi), recs, max_recs, res)
         if rc != 0:
             raise SystemExit("mgDistRunCycleFile failed: %d %s" % (rc, lib.mgLastError().decode()))
         return res.launches
@@ -615,18 +618,18 @@ def multi_gpu_arm(args, mg, api, cycles, lib, torch, dist, stream, rank, world, 
         del hF, hU
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "Vcycle.txt shape (con_step=3, con_N=1, GS 1e-7 opt 1) at N_max=%d N_min=8: one grid row-slab "
-                               "partitioned over %d GPUs, 16384^2 fine points per GPU" % (N, world),
-                   "value_is": "V-cycles/s x (N_max/16384)^2, i.e. in units of the 1-GPU workload",
+        "config": {"workload": (wl["what"] % N) + ": one grid row-slab partitioned over %d GPUs%s" % (world, ", 16384^2 fine points per GPU" if weak else ""),
+                   "name": args.config,
+                   "value_is": "V-cycles/s x (N_max/16384)^2, i.e. in units of the 1-GPU workload" if weak else "cycles/s of the whole grid",
                    "driver": "mgDistRunCycleFile: fused nodes on row slabs; the %d halo rows go into the neighbours' slabs by peer stores "
                              "of the fused kernel itself (CUDA IPC over NVLink, flag words + stream waits, no communication kernel); levels "
                              "< %d rows: source broadcast to every rank, coarse sub-cycle redundant on every rank" % (8, threshold),
                    "l2": "inputs exceed L2", "parallelism": "row slabs x%d" % world},
         "fine_dof_cycles_per_s": n * 1000.0 / ms_per_step, "global_ms_per_cycle": ms_per_step, "mg_error": mg_error,
-        "trace_errors": [t["err"] for t in trace if t["node"] != 0], "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+        "trace_errors": [t["err"] for t in trace if t["node"] != 0][:48], "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": "whole V-cycle on slabs (fused nodes)", "achieved": 44.0 * n * 4 / 3 / (ms_per_step * 1e6) / world,
                      "peak": hbm_peak, "unit": "GB/s", "frac": 44.0 * n * 4 / 3 / (ms_per_step * 1e6) / world / hbm_peak, "traffic": None,
                      "note": "per GPU: compulsory bytes of the fused cycle (44 B per fine point per level, ladder sum 4/3) / time; "

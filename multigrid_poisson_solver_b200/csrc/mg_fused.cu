@@ -273,7 +273,7 @@ void launch_stream(StreamParams &p)
     using G = StreamGeo<S, ERR || RES, RES>;
     constexpr int STREAM_WARPS = stream_shape(RES).warps, STREAM_MIN_CTAS = stream_shape(RES).min_ctas;
     static bool opted_in = false;   // one flag per instantiation
-    launch_stream_kernel(k_stream<S, IN, ERR, RES>, p, G::W, STREAM_WARPS, STREAM_MIN_CTAS, stream_smem_bytes(IN, STREAM_WARPS), ERR, 2 * S + 3,
+    launch_stream_kernel(k_stream<S, IN, ERR, RES>, p, G::W, STREAM_WARPS, STREAM_MIN_CTAS, stream_smem_bytes(IN, STREAM_WARPS, RES), ERR, 2 * S + 3,
                          opted_in);
 }
 

@@ -12,7 +12,7 @@ template <int S, int IN, bool ERR, bool RES>
 void launch_one(StreamParams &p)
 {
     using G = StreamGeo<S, ERR || RES, RES>;
-    constexpr int warps = stream_shape(RES).warps, ctas = stream_shape(RES).min_ctas, smem = stream_smem_bytes(IN, warps);
+    constexpr int warps = stream_shape(RES).warps, ctas = stream_shape(RES).min_ctas, smem = stream_smem_bytes(IN, warps, RES);
     const int blocks = stream_launch_prepare(p, G::W, warps, ctas, ERR, 2 * S + 3);
     if (blocks == 0) return;
     static bool opted_in = false;   // one flag per instantiation
@@ -41,7 +41,7 @@ template <int IN, bool RES, bool PEER>
 void launch_mid(StreamParams &p)
 {
     using G = StreamGeo<2, true, RES>;
-    constexpr int warps = stream_shape(RES).warps, ctas = stream_shape(RES).min_ctas, smem = stream_smem_bytes(IN, warps);
+    constexpr int warps = stream_shape(RES).warps, ctas = stream_shape(RES).min_ctas, smem = stream_smem_bytes(IN, warps, RES);
     const int blocks = stream_launch_prepare(p, G::W, warps, ctas, true, 2 * 2 + 3);
     if (blocks == 0) return;
     static bool opted_in = false;

@@ -69,10 +69,14 @@ constexpr int STREAM_SMAX = 3;          // sweeps fused per pass
 constexpr int STREAM_DEPTH = MG_STREAM_DEPTH;   // rows in flight per warp (cp.async ring in shared memory), power of two
 // shared memory: [warp][slot][U | F (| coarse row, 1 node only)][lane] x 16 B
 // the 1 node adds the staged coarse row (512 B) and the row's {row_w, row_cell} entry (32 B)
-__host__ __device__ constexpr int stream_slot_bytes(int in) { return in == 2 ? 3 * 512 + 32 : 2 * 512; }
-__host__ __device__ constexpr int stream_smem_bytes(int in, int warps)
+// RES: 16 more bytes hold the restriction table entry of the fine row the step pairs up, copied by lane 0 and read by all
+// lanes (a __syncwarp on each side).  It used to be a global load one step ahead: a quarter of all stall samples of the
+// -1 node sat on the F2I that consumes it (ncu, long scoreboard).  (32 lanes copying the same 16 bytes each is not an
+// option: same-address LDGSTS serialise -- measured 2.7x slower.)
+__host__ __device__ constexpr int stream_slot_bytes(int in, bool res = false) { return in == 2 ? 3 * 512 + 32 : res ? 2 * 512 + 32 : 2 * 512; }
+__host__ __device__ constexpr int stream_smem_bytes(int in, int warps, bool res = false)
 {
-    return warps * (STREAM_DEPTH * stream_slot_bytes(in) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
+    return warps * (STREAM_DEPTH * stream_slot_bytes(in, res) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
 }
 
 struct StreamParams {
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     // STREAM_DEPTH rows of U and F in flight per warp at no register cost.  Each lane copies
     // and later reads back only its own 16 bytes, so no barrier is involved, only wait_group.
     extern __shared__ __align__(16) unsigned char stream_smem[];
-    constexpr int SLOT_BYTES = stream_slot_bytes(IN);   // [U | F | coarse row][lane] x 16 B
+    constexpr int SLOT_BYTES = stream_slot_bytes(IN, RES);   // [U | F | coarse row or restriction table entry][lane] x 16 B
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(stream_smem);
     const unsigned warp_ring = smem0 + warp * (STREAM_DEPTH * SLOT_BYTES);
     const unsigned ring_base = warp_ring + lane * 16;
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     int ccx = -1, ccy = -1;
     double ax = 0.0, ay = 0.0;
     bool zx = true, zy = true;                   // coarse column on the coarse boundary: value forced to 0
-    double2 rinfo_next = make_double2(-1.0, 0.0);   // {coarse row, weight} of the fine row the NEXT step pairs up
+
     if (RES && col_own) {
         ccx = p.f2c[cx];
         ccy = p.f2c[cx + 1];
@@ -393,10 +397,6 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         zy = ccy == 0 || ccy == p.M - 1;
     }
     const bool res_even = MG_RES_EVEN && RES && __all_sync(0xffffffffu, ccy < 0);   // nested ladder: coarse points at even fine columns only
-    if (RES && active) {
-        const int f0 = r_first - S - 2;           // the fine row step r_first pairs with the one above it
-        if (f0 >= 0 && f0 <= N - 1) rinfo_next = p.rrow[f0];
-    }
     // ---- prolongation state
     // Coarse rows are staged through the third part of each ring slot: the slot of fine row r
     // holds doubles [cbase, cbase+64) of coarse row row_cell[r]+1 (the upper row of its cell).
@@ -443,6 +443,11 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         if (NF > 0) {
             const bool ok = col_ok && r - 1 >= p.row0 && r - 1 < p.row0 + p.rows;
             cp_async16(ring_base + off + 512, ok ? (const void *)(Fp + (ptrdiff_t)(r - 1) * ldn + cx) : (const void *)p.F_valid, ok);
+        }
+        if (RES && lane == 0) {                          // {coarse row or -1, weight} of fine row r-S-2: what step r pairs with the row above
+            const int fr_ = r - S - 2;
+            const bool ok = fr_ >= 0 && fr_ <= N - 1;
+            cp_async16(warp_ring + off + 1024, ok ? (const void *)(p.rrow + fr_) : (const void *)p.F_valid, ok);
         }
         if (IN == IN_PROLONG) {
             const int c0 = cbase + 2 * lane;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         for (int k = 0; k < U; ++k) {
             const int r = rb + k;
             bool bad = false;
-            double2 x = make_double2(0.0, 0.0), f_new = x;
+            double2 x = make_double2(0.0, 0.0), f_new = x, ri_cur = make_double2(-1.0, 0.0);
             if (IN == IN_PROLONG) {
                 // level 0 of row r was produced one step ago; produce row r+1 now, next to this row's sweeps
                 cp_async_wait<STREAM_DEPTH - 2>();                // the groups of rows r and r+1 have landed
@@ -540,14 +545,20 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 bad = prolong_from_slot(slot_n);
             } else {
                 cp_async_wait<STREAM_DEPTH - 1>();                // the group of row r has landed
+                if (RES) __syncwarp();                            // ... lane 0's table entry for every lane
                 if (IN != IN_ZERO) x = lds2(ring_base + slot_off);
                 if (NF > 0) f_new = lds2(ring_base + slot_off + 512);
+                if (RES) {
+                    ri_cur = lds2(warp_ring + slot_off + 1024);
+                    __syncwarp();                                 // every lane has read it: lane 0 may refill the slot
+                }
             }
 
             // refill the slot with row r + DEPTH (the values above are in registers by now)
             if (FAST) {
                 if (IN != IN_ZERO) cp_async16(ring_base + slot_off, Up + (ptrdiff_t)(r + STREAM_DEPTH) * ldn + cx);
                 if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
+                if (RES && lane == 0) cp_async16(warp_ring + slot_off + 1024, p.rrow + (r + STREAM_DEPTH - S - 2));
                 if (IN == IN_PROLONG) {
                     const int c0 = cbase + 2 * lane;
                     const double *src = p.Uc + (ptrdiff_t)min(max(cell_of_row(r + STREAM_DEPTH) + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
@@ -647,10 +658,8 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 if (RES) {
                     const double2 d_cur = make_double2(-res.x, -res.y);   // D = -D (:277-280)
                     const int f_row = rho - 1;                            // lower fine row of the pair (f_row, rho)
-                    const double2 ri = rinfo_next;                        // {coarse row of f_row or -1, its weight}
-                    if (FAST || (f_row + 1 >= 0 && f_row + 1 <= N - 1)) rinfo_next = p.rrow[f_row + 1];
-                    else rinfo_next = make_double2(-1.0, 0.0);
-                    const int crow = (int)ri.x;
+                    const double2 ri = ri_cur;                            // {coarse row of f_row or -1, its weight}, staged with the row
+                    const int crow = (FAST || (f_row >= 0 && f_row <= N - 1)) ? (int)ri.x : -1;
                     if (crow >= 0 && f_row >= own_r_lo && f_row < own_r_hi) {   // warp-uniform
                         const double cw = ri.y;
                         const bool row_edge = crow == 0 || crow == p.M - 1;
