@@ -670,7 +670,7 @@ def dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, unfu
         return e0.elapsed_time(e1) / reps
 
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = {k.split()[0]: v["traffic"] for k, v in json.load(f).items()}
@@ -698,7 +698,7 @@ def dominant_kernel_roofline(lib, mg, stream, torch, N, hbm_peak, peak_src, unfu
     return {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved"], "peak": hbm_peak, "unit": "GB/s",
             "frac": top["frac"], "traffic": top["traffic"], "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
             "ms_per_launch": top["ms_per_launch"], "peak_source": peak_src, "grid": "N=%d fine level" % N,
-            "traffic_source": "profiles/r01_kernel_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
+            "traffic_source": "profiles/r02_kernel_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
             "kernels": kernels}
 
 

@@ -167,6 +167,8 @@ const SegmentTable &segment_table(int rows, int n_strips, int resident_warps, in
 // MG_TILE_MAX_N / mgSetTileMaxN(n >= 0) route every size up to n through it (0 disables it).
 int g_tile_max_N = 1024;
 bool g_tile_even = false;
+int g_tile_odd_max_N = 1 << 30;   // ODD sizes of any extent take the tile kernel (the streaming kernels need 16-byte aligned rows); the
+                                  // alternative is one kernel per operator (~12 launches and ~6x the traffic per node)
 int g_cols4 = 1;   // 4 columns per lane (mg_stream4.cuh) for the passes that have a variant; MG_COLS4=0 disables
 int g_strip = 1;   // the bulk-copy 4-column kernel (mg_strip.cuh, instantiated in mg_legs.cu) for smoothing passes; MG_STRIP=0: never
 int g_strip_min_N = 8192;   // ... from this grid size on (MG_STRIP_MIN_N)
@@ -233,14 +235,14 @@ void launch_stream_kernel(Kernel kernel, StreamParams &p, int W, int warps, int 
     }
 }
 
-// Small whole grids: one CTA per 32 x 32 tile instead of one warp per strip (mg_tile.cuh).
+// Whole grids of odd size (any extent) or, when asked for, small even ones: one CTA per 32 x 32 tile instead of one warp per strip (mg_tile.cuh).
+bool tile_ok_size(int N) { return (N % 2 != 0) ? N <= g_tile_odd_max_N : (g_tile_even && N <= g_tile_max_N); }
 bool tile_ok(const StreamParams &p)
 {
-    return g_tile_max_N > 0 && p.N <= g_tile_max_N && (g_tile_even || p.N % 2 != 0) && p.row0 == 0 && p.rows == p.N && p.own_lo == 0 && p.own_hi == p.N &&
+    return tile_ok_size(p.N) && p.row0 == 0 && p.rows == p.N && p.own_lo == 0 && p.own_hi == p.N &&
            !p.raw_sum && !p.subset && !p.err_add;
 }
 
-bool tile_ok_size(int N) { return g_tile_max_N > 0 && N <= g_tile_max_N && (g_tile_even || N % 2 != 0); }
 
 template <int S, int IN, bool ERR, bool RES>
 void launch_tile(StreamParams &p)
@@ -315,7 +317,7 @@ void launch_stream_any(int S, int in, int mode, StreamParams &p)
 
 bool streamable(int N) { return !g_disable && N >= 4 && (N % 2 == 0); }
 // a whole grid the fused passes can serve: even (streaming kernel) or small (tile kernel, any parity)
-bool fusable(int N) { return !g_disable && N >= 4 && (N % 2 == 0 || N <= g_tile_max_N); }
+bool fusable(int N) { return !g_disable && N >= 4 && (N % 2 == 0 || N <= g_tile_odd_max_N); }
 
 // Split `step` sweeps into passes of at most STREAM_SMAX, as evenly as possible.
 std::vector<int> split_passes(int step)
@@ -672,14 +674,14 @@ void fused_init()
     if (const char *d = getenv("MG_STRIP")) g_strip = atoi(d);
     if (const char *d = getenv("MG_STRIP_MIN_N")) g_strip_min_N = atoi(d);
     if (const char *d = getenv("MG_SPLIT_MIN_POINTS")) g_split_min_points = atoll(d);
-    if (const char *d = getenv("MG_TILE_MAX_N")) { g_tile_max_N = std::max(0, atoi(d)); g_tile_even = true; }
+    if (const char *d = getenv("MG_TILE_MAX_N")) { g_tile_max_N = g_tile_odd_max_N = std::max(0, atoi(d)); g_tile_even = true; }
 }
 
 int set_tile_max_n(int n)
 {
     const int old = g_tile_even ? g_tile_max_N : -1;
-    if (n >= 0) { g_tile_max_N = n; g_tile_even = true; }      // every size up to n (0: never)
-    else        { g_tile_max_N = 1024; g_tile_even = false; }   // default: odd sizes up to 1024
+    if (n >= 0) { g_tile_max_N = g_tile_odd_max_N = n; g_tile_even = true; }      // every size up to n (0: never)
+    else        { g_tile_max_N = 1024; g_tile_odd_max_N = 1 << 30; g_tile_even = false; }   // default: odd sizes only, any extent
     return old;
 }
 
