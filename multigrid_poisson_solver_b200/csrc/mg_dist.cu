@@ -294,8 +294,11 @@ size_t slab_bytes(const LevelGeom &g, int rank)
 
 // ------------------------------------------------------------------ the fabric: arenas + flag words of all ranks
 // Flag words of a rank (unsigned int): [0] pass number published by the rank below, [1] by the rank above,
-// [2 + s] gather number published by source rank s, [2 + MAX_WORLD] set when a peer gave up (error).
-constexpr int W_FROM_LO = 0, W_FROM_HI = 1, W_GATHER = 2, W_ABORT = 2 + MAX_WORLD, N_WORDS = 64;
+// [2 + s] gather number published by source rank s, [2 + MAX_WORLD + s] scalar-exchange number of source rank s,
+// [2 + 2 MAX_WORLD] set when a peer gave up (error).
+constexpr int W_FROM_LO = 0, W_FROM_HI = 1, W_GATHER = 2, W_SCAL = 2 + MAX_WORLD, W_ABORT = 2 + 2 * MAX_WORLD, N_WORDS = 64;
+constexpr int SCAL_N = 64;                                            // doubles per rank in the scalar exchange
+constexpr size_t SCAL_TABLE_BYTES = 2 * MAX_WORLD * SCAL_N * sizeof(double);   // [parity][source rank][SCAL_N], at the bottom of every arena
 
 __global__ void k_peer_bcast(const double *src, size_t count, int n_dst, const double *const *dst_table, unsigned int *const *flag_table,
                              unsigned int flag_val, unsigned int *ticket)
@@ -326,11 +329,11 @@ __global__ void k_peer_bcast(const double *src, size_t count, int n_dst, const d
 }
 
 // one warp: lane s waits until source rank s has published gather number >= want (or a peer aborted)
-__global__ void k_wait_gather(const unsigned int *words, int world, int self, unsigned int want)
+__global__ void k_wait_gather(const unsigned int *words, int first_word, int world, int self, unsigned int want)
 {
     const int s = threadIdx.x;
     if (s >= world || s == self) return;
-    const unsigned int *w = words + W_GATHER + s;
+    const unsigned int *w = words + first_word + s;
     unsigned int *abort_w = const_cast<unsigned int *>(words) + W_ABORT;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -370,7 +373,9 @@ public:
         const double *dst_h[2][MAX_WORLD] = {};
         unsigned int *flag_h[2][MAX_WORLD] = {};
     };
-    std::vector<Tables> tables;            // [local index]
+    std::vector<Tables> tables;            // [local index]: the gather broadcast
+    std::vector<Tables> stables;           // [local index]: the scalar exchange
+    unsigned int exchanges = 0;            // scalar exchanges so far
 
     explicit Fabric(Comm &c) : comm(c), world(c.world), peer((size_t)c.world), top((size_t)c.world, 0)
     {
@@ -383,9 +388,11 @@ public:
             peer[r].words = w;
         }
         tables.resize(comm.local.size());
-        for (auto &t : tables)
-            for (int k = 0; k < 2; ++k)
-                if (cudaMalloc(&t.dst[k], MAX_WORLD * sizeof(double *)) != cudaSuccess || cudaMalloc(&t.flag[k], MAX_WORLD * sizeof(unsigned int *)) != cudaSuccess) ok = false;
+        stables.resize(comm.local.size());
+        for (auto *set : {&tables, &stables})
+            for (auto &t : *set)
+                for (int k = 0; k < 2; ++k)
+                    if (cudaMalloc(&t.dst[k], MAX_WORLD * sizeof(double *)) != cudaSuccess || cudaMalloc(&t.flag[k], MAX_WORLD * sizeof(unsigned int *)) != cudaSuccess) ok = false;
         cudaDeviceSynchronize();
         ok = exchange(false) && ok;
     }
@@ -408,8 +415,11 @@ public:
             }
         }
         if (words_too)
-            for (auto &t : tables)
-                for (int k = 0; k < 2; ++k) { cudaFree(t.dst[k]); cudaFree(t.flag[k]); t.dst[k] = nullptr; t.flag[k] = nullptr; }
+            for (auto *set : {&tables, &stables})
+                for (auto &t : *set)
+                    for (int k = 0; k < 2; ++k) { cudaFree(t.dst[k]); cudaFree(t.flag[k]); t.dst[k] = nullptr; t.flag[k] = nullptr; }
+        for (auto *set : {&tables, &stables})        // the arenas move: cached destination tables are stale
+            for (auto &t : *set) { memset(t.dst_h, 0, sizeof t.dst_h); memset(t.flag_h, 0, sizeof t.flag_h); }
         cap = 0;
     }
 
@@ -469,7 +479,10 @@ public:
     }
     template <class T>
     T *at(int rank, size_t off) const { return reinterpret_cast<T *>(peer[rank].arena + off); }
-    size_t gather_off(unsigned int g) const { return (size_t)(g & 1u) * gather_bytes; }   // double-buffered by gather parity
+    // bottom of every arena: the scalar-exchange table, then two gather buffers (double-buffered by gather parity), then the level stack
+    size_t scal_off(unsigned int x, int src) const { return ((size_t)(x & 1u) * MAX_WORLD + (size_t)src) * SCAL_N * sizeof(double); }
+    size_t gather_off(unsigned int g) const { return SCAL_TABLE_BYTES + (size_t)(g & 1u) * gather_bytes; }
+    size_t stack_base() const { return SCAL_TABLE_BYTES + 2 * gather_bytes; }
 
     void wait32(cudaStream_t st, unsigned int *addr, unsigned int value)
     {
@@ -517,7 +530,7 @@ public:
             st.scal = (double *)pool_alloc(64 * sizeof(double));
             ranks.push_back(st);
         }
-        std::fill(fab.top.begin(), fab.top.end(), 2 * fab.gather_bytes);   // the two gather buffers sit at the bottom
+        std::fill(fab.top.begin(), fab.top.end(), fab.stack_base());        // the exchange table and the gather buffers sit at the bottom
     }
     ~DistCycle()
     {
@@ -591,13 +604,51 @@ public:
         return induce_geometry(fine, M, comm.world, threshold_, coarse, why);
     }
 
-    // sum the ranks' partials at scal[idx .. idx+n); every local rank ends with the global sums
-    void allreduce(int idx, int n = 1)
+    // Scalar exchange without a collective library: every rank stores its SCAL_N partials into every rank's table (peer
+    // stores by the small broadcast kernel, flag per source rank), waits for everybody else's, and copies the table of this
+    // exchange to `host` ([world][SCAL_N], queued on the stream).  The caller adds the ranks' values IN RANK ORDER after a
+    // synchronisation: the same association on every rank and in every run, so all ranks take the same decisions.
+    void exchange(double *host)
     {
-        if (comm.world == 1) return;
-        std::vector<double *> v;
-        for (auto &st : ranks) v.push_back(st.scal + idx);
-        comm.allreduce_sum(v, n, ctx().stream);
+        Context &c = ctx();
+        const unsigned int x = ++fab.exchanges;
+        const int par = (int)(x & 1u);
+        for (size_t i = 0; i < ranks.size(); ++i) {
+            const int r = ranks[i].rank;
+            const double *dst_h[MAX_WORLD] = {};
+            unsigned int *flag_h[MAX_WORLD] = {};
+            for (int q = 0; q < comm.world; ++q) {          // (its own table too: a local store)
+                dst_h[q] = fab.at<double>(q, fab.scal_off(x, r));
+                flag_h[q] = fab.peer[q].words + W_SCAL + r;
+            }
+            Fabric::Tables &t = fab.stables[i];
+            if (memcmp(t.dst_h[par], dst_h, sizeof dst_h) || memcmp(t.flag_h[par], flag_h, sizeof flag_h)) {
+                memcpy(t.dst_h[par], dst_h, sizeof dst_h);
+                memcpy(t.flag_h[par], flag_h, sizeof flag_h);
+                check(cudaMemcpyAsync(t.dst[par], dst_h, sizeof dst_h, cudaMemcpyHostToDevice, c.stream), "H2D exchange table");
+                check(cudaMemcpyAsync(t.flag[par], flag_h, sizeof flag_h, cudaMemcpyHostToDevice, c.stream), "H2D exchange table");
+            }
+            k_peer_bcast<<<1, 64, 0, c.stream>>>(ranks[i].scal, SCAL_N, comm.world, t.dst[par], t.flag[par], x, c.counters + 12);
+            c.launches++;
+            check(cudaGetLastError(), "k_peer_bcast (scalars)");
+        }
+        for (size_t i = 0; i < ranks.size(); ++i) {
+            const int r = ranks[i].rank;
+            if (comm.world > 1) {
+                k_wait_gather<<<1, 32, 0, c.stream>>>(fab.peer[r].words, W_SCAL, comm.world, r, x);
+                c.launches++;
+                check(cudaGetLastError(), "k_wait_gather (scalars)");
+            }
+        }
+        const int r0 = ranks[0].rank;
+        check(cudaMemcpyAsync(host, fab.at<double>(r0, fab.scal_off(x, 0)), (size_t)comm.world * SCAL_N * sizeof(double), cudaMemcpyDeviceToHost, c.stream),
+              "D2H exchange table");
+    }
+    static double rank_sum(const double *table, int world, int idx)
+    {
+        double s = 0.0;
+        for (int q = 0; q < world; ++q) s += table[(size_t)q * SCAL_N + idx];
+        return s;
     }
 
     // One fused pass over every local slab of distributed level `li`: S sweeps from U (in_mode 0), from zero (1) or
@@ -697,7 +748,7 @@ public:
         }
         for (size_t i = 0; i < ranks.size(); ++i) {
             const int r = ranks[i].rank;
-            k_wait_gather<<<1, 32, 0, c.stream>>>(fab.peer[r].words, comm.world, r, g);
+            k_wait_gather<<<1, 32, 0, c.stream>>>(fab.peer[r].words, W_GATHER, comm.world, r, g);
             c.launches++;
             check(cudaGetLastError(), "k_wait_gather");
         }
@@ -863,7 +914,7 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
         if (prc == 21) fail(-41, "the exact solver runs on an agglomerated level: lower the coarsest size or raise the threshold");
         if (prc) return prc;
         const size_t g_need = std::max(gather_need, fab.gather_bytes);
-        if (!fab.reserve(2 * g_need + arena_need, g_need)) return 30;
+        if (!fab.reserve(SCAL_TABLE_BYTES + 2 * g_need + arena_need, g_need)) return 30;
     }
 
     DistCycle cy(comm, fab, threshold);
@@ -907,16 +958,16 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
         return r;
     };
     constexpr int SCAL_BATCH = 48;
+    static double *xtable = nullptr;               // pinned: [world][SCAL_N] table of the last scalar exchange
+    if (!xtable && !check(cudaHostAlloc(&xtable, MAX_WORLD * SCAL_N * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc exchange table")) return 30;
     std::vector<std::pair<int, int>> deferred;     // (trace record, scal slot) holding a raw red-parity sum
     auto harvest = [&]() {
         if (cy.scal_used_ > 0) {
-            double sums[SCAL_BATCH];
-            cy.allreduce(0, cy.scal_used_);
-            check(cudaMemcpyAsync(sums, cy.ranks[0].scal, cy.scal_used_ * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H sums");
+            cy.exchange(xtable);
             check(cudaStreamSynchronize(c.stream), "sync");
             for (const auto &d : deferred) {
                 if (!recs || d.first >= max_recs) continue;
-                const double v = sums[d.second], N = recs[d.first].N;
+                const double v = DistCycle::rank_sum(xtable, comm.world, d.second), N = recs[d.first].N;
                 recs[d.first].err = (v + v) / N / N;                      // (sum1+sum2)/N/N, :621-622
             }
             deferred.clear();
@@ -931,11 +982,9 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
     };
     // all-reduce scal[idx] and wait for the value on the host (trigger loops)
     auto reduced_now = [&](int idx) {
-        cy.allreduce(idx);
-        double s = 0.0;
-        check(cudaMemcpyAsync(&s, cy.ranks[0].scal + idx, sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+        cy.exchange(xtable);
         check(cudaStreamSynchronize(c.stream), "sync");
-        return s;
+        return DistCycle::rank_sum(xtable, comm.world, idx);
     };
     const std::vector<const double *> no_uc;
     const std::vector<Slab> no_slab;
@@ -956,11 +1005,10 @@ int run_dist(Comm &comm, Fabric &fab, const char *path, int threshold, int flags
             const int idx = cy.scal_used_;
             cy.scal_used_ += 2;
             cy.pass(li, L, 2, mode, true, idx, M, with_fc, fc_dist, cb, fc_full, mode == 2 ? Nc : 0, mode == 2 ? uc : no_uc, mode == 2 ? uc_slab : no_slab, true);
-            cy.allreduce(idx, 2);
-            double s[2] = {0.0, 0.0};
-            check(cudaMemcpyAsync(s, cy.ranks[0].scal + idx, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream), "D2H");
+            cy.exchange(xtable);
             check(cudaStreamSynchronize(c.stream), "sync");
             if (c.err_code) break;
+            const double s[2] = {DistCycle::rank_sum(xtable, comm.world, idx), DistCycle::rank_sum(xtable, comm.world, idx + 1)};
             const double e2 = (s[0] + s[0]) / N / N, e1 = (s[1] + s[1]) / N / N;
             if (done + 1 > 1 && std::fabs(e1 - prev) <= TRIGGER) {       // the loop ends after the first of these two sweeps
                 cy.unswap(li);
@@ -1337,8 +1385,8 @@ int mgDistSmoothStress(int N, double L, int step, int reps, double *ms_per_rep, 
     // arena: U and W slabs of every rank (F is local); a local allocation failure travels through the collective reserve
     size_t need = 0;
     for (int r = 0; r < comm.world; ++r) need = std::max(need, 2 * slab_bytes(g, r));
-    if (!fab.reserve(2 * fab.gather_bytes + need, fab.gather_bytes)) return 3;
-    std::fill(fab.top.begin(), fab.top.end(), 2 * fab.gather_bytes);
+    if (!fab.reserve(fab.stack_base() + need, fab.gather_bytes)) return 3;
+    std::fill(fab.top.begin(), fab.top.end(), fab.stack_base());
     std::vector<size_t> bytes((size_t)comm.world);
     for (int r = 0; r < comm.world; ++r) bytes[r] = slab_bytes(g, r);
     std::vector<size_t> offU = fab.alloc(bytes), offW = fab.alloc(bytes);

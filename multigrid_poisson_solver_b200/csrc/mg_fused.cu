@@ -442,9 +442,9 @@ int restrict_first_coarse_at_or_after(int N, int M, int fine_row)
 
 // A slab pass with peer memory is launched in two parts: the thin row segments at both ends of the owned range -- they
 // produce every row a neighbour keeps as a halo, also of the restricted grid (8 coarse rows <= 22 fine rows up to ratio
-// 2.5) -- with the peer-store instantiation, then the interior with the plain kernel, which publishes the pass number
-// when it has drained.  The halo rows cross NVLink while the interior is swept, and the bulk of the pass runs the very
-// kernel of the single-GPU path (the peer-store variants cost 5-10 %: measured).  Slabs too thin to split: one launch.
+// 2.5) -- with the peer-store instantiation, then the interior with the plain kernel.  The halo rows cross NVLink while
+// the interior is swept, and the bulk of the pass runs the very kernel of the single-GPU path (the peer-store variants
+// cost 5-10 %: measured).  Slabs too thin to split: one launch.
 template <class Launch>
 void launch_slab(const StreamParams &base, const PeerLinks &peers, Launch launch)
 {
@@ -456,13 +456,17 @@ void launch_slab(const StreamParams &base, const PeerLinks &peers, Launch launch
     const bool stores = peers.U_lo || peers.U_hi || peers.Fc_lo || peers.Fc_hi;
     // (small slabs are latency bound: a second launch costs more than the peer-store variant does)
     if (stores && segments_splittable(base.own_hi - base.own_lo) && (long long)(base.own_hi - base.own_lo) * base.N >= g_split_min_points) {
+        // The pass number is published by the EDGE launch: once it has drained, every row a neighbour needs has been stored
+        // into its slab, and this rank's own halo rows -- read by the edge segments only (the interior keeps >= 48 rows away
+        // from both ends) -- are free to be overwritten by the neighbours' next pass.  The interior launches of different
+        // ranks therefore never wait for one another: skew between ranks is absorbed instead of amplified.
         StreamParams a = base, b = base;
         a.subset = 1;
         with_peers(a);
+        with_flags(a);
         launch(a);
         b.subset = 2;
         b.err_add = b.err_dev ? 1 : 0;           // the interior adds its error sum(s) to the edge launch's
-        with_flags(b);
         launch(b);
     } else {
         StreamParams q = base;
