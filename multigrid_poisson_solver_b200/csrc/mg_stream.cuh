@@ -366,7 +366,9 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     // all row indices below are GLOBAL; the arrays are addressed with (row - row0)
     const int2 seg_rows = __ldg(p.segs + seg);                  // rows of the segment relative to own_lo
     const int own_r_lo = p.own_lo + seg_rows.x, own_r_hi = p.own_lo + seg_rows.y;
-    const int r_first = max(0, own_r_lo - G::ROW_LEAD);
+    // even, so that the parity of every row index of an unrolled chunk is a compile-time fact (the red-parity error
+    // then needs the residual of ONE of the lane's two columns); the extra leading row is one more warm-up row
+    const int r_first = max(0, own_r_lo - G::ROW_LEAD) & ~1;
     const int r_last = min(own_r_hi - 1 + G::ROW_TAIL, N - 1 + G::ROW_LEAD);
     // rows of this task whose output is also a neighbour's halo (slabs with peer memory)
     const bool peer_rows = PEER && ((p.peer_U_lo && own_r_lo < p.u_lo_end) || (p.peer_U_hi && own_r_hi > p.u_hi_begin));
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     if (IN == IN_PROLONG && active) {
         const int rq_first = __shfl_sync(0xffffffffu, tab, 0);
         // lower coarse row of the first cell: the only one that is not staged
-        const double *c_lo = p.Uc + (ptrdiff_t)rq_first * p.Nc;
+        const double *c_lo = p.Uc + (ptrdiff_t)max(rq_first, p.uc_row0) * p.Nc;   // (clamped: only a warm-up row can ask for less)
         if (col_ok) {
             const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
             top.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
@@ -609,10 +611,11 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                     }
                     if (MID && t == 1) {
                         // the smoothing error of level 1 (after the first sweep): its row i is the centre of this very stencil
-                        double v = (i & 1) ? residual_fast(c.y, s4y, f.y, inv_h2) : residual_fast(c.x, s4x, f.x, inv_h2);   // red point (:609-611)
+                        const bool i_odd = (k & 1) != 0;              // i = rb + k - 2, rb even
+                        double v = i_odd ? residual_fast(c.y, s4y, f.y, inv_h2) : residual_fast(c.x, s4x, f.x, inv_h2);   // red point (:609-611)
                         if (!FAST) {
                             const bool row_in = i > 0 && i < N - 1;
-                            v = (row_in && ((i & 1) ? y_in : x_in)) ? v : 0.0;
+                            v = (row_in && (i_odd ? y_in : x_in)) ? v : 0.0;
                         }
                         const bool take = col_own && i >= own_r_lo && i < own_r_hi;
                         mid_acc = __dadd_rn(mid_acc, take ? fabs(v) : 0.0);
@@ -639,10 +642,16 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 const int rho = r - S - 1;                        // residual row
                 const double2 below = w[S][k & 1], c = w[S][(k & 1) ^ 1];
                 const double2 f = fr[(k - S + 4 * NR) % NR];
-                const double left = shfl_up1(c.y), right = shfl_dn1(c.x);
-                double2 res;
-                res.x = residual_fast(c.x, sum4(x.x, below.x, c.y, left), f.x, inv_h2);
-                res.y = residual_fast(c.y, sum4(x.y, below.y, right, c.x), f.y, inv_h2);
+                const bool rho_odd = ((k + S + 1) & 1) != 0;      // rb is even: known after unrolling
+                double2 res = make_double2(0.0, 0.0);
+                if (RES || !rho_odd) {                            // (without RES only the red column's residual is needed)
+                    const double left = shfl_up1(c.y);
+                    res.x = residual_fast(c.x, sum4(x.x, below.x, c.y, left), f.x, inv_h2);
+                }
+                if (RES || rho_odd) {
+                    const double right = shfl_dn1(c.x);
+                    res.y = residual_fast(c.y, sum4(x.y, below.y, right, c.x), f.y, inv_h2);
+                }
                 if (!FAST) {                                      // 0 on the boundary (:559)
                     const bool row_in = rho > 0 && rho < N - 1;
                     res.x = (row_in && x_in) ? res.x : 0.0;
@@ -651,7 +660,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 w[S][k & 1] = x;
                 if (ERR) {
                     // red = (row + column) even: exactly one of the lane's two columns (:609-611)
-                    const double v = (rho & 1) ? res.y : res.x;   // cx is even
+                    const double v = rho_odd ? res.y : res.x;     // cx is even
                     const bool take = col_own && rho >= own_r_lo && rho < own_r_hi;
                     err_acc = __dadd_rn(err_acc, take ? fabs(v) : 0.0);   // + 0.0 is exact
                 }

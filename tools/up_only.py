@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Runs mgUpLeg alone a few times (profiling target): python tools/up_only.py N reps"""
+"""Runs mgUpLeg alone a few times (profiling target, A/B of library variants with MG_LIB_NAME): python tools/up_only.py N reps"""
 import os
 import sys
 
@@ -25,5 +25,18 @@ e0.record(stream)
 for _ in range(reps):
     lib.mgUpLeg(M, Uc.ptr, N, 1.0, U.ptr, W.ptr, F.ptr, 3, slot)
 e1.record(stream)
+clk, pw = [], []
+try:                                   # SM clock / power while the launches run (the 1 node is issue bound: clock sensitive)
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    while not e1.query():
+        clk.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        pw.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+except Exception:
+    pass
 lib.mgSync()
-print("up N=%d H=%s G=%s: %.4f ms" % (N, os.environ.get("MG_STREAM_H", "auto"), os.environ.get("MG_SCHED_G", "-"), e0.elapsed_time(e1) / reps))
+clk.sort()
+print("up N=%d lib=%s H=%s: %.4f ms  sm_mhz median %s min %s  power max %s W" % (
+    N, os.environ.get("MG_LIB_NAME", "libmgb200.so"), os.environ.get("MG_STREAM_H", "auto"), e0.elapsed_time(e1) / reps,
+    clk[len(clk) // 2] if clk else "?", clk[0] if clk else "?", ("%.0f" % max(pw)) if pw else "?"))
