@@ -76,7 +76,7 @@ constexpr int STREAM_DEPTH = MG_STREAM_DEPTH;   // rows in flight per warp (cp.a
 __host__ __device__ constexpr int stream_slot_bytes(int in, bool res = false) { return in == 2 ? 3 * 512 + 32 : res ? 2 * 512 + 32 : 2 * 512; }
 __host__ __device__ constexpr int stream_smem_bytes(int in, int warps, bool res = false)
 {
-    return warps * (STREAM_DEPTH * stream_slot_bytes(in, res) + (in == 2 ? 1024 : 0));   // + per-lane prolongation weights
+    return warps * STREAM_DEPTH * stream_slot_bytes(in, res);
 }
 
 struct StreamParams {
@@ -340,7 +340,6 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(stream_smem);
     const unsigned warp_ring = smem0 + warp * (STREAM_DEPTH * SLOT_BYTES);
     const unsigned ring_base = warp_ring + lane * 16;
-    const unsigned wc_addr = smem0 + STREAM_WARPS * (STREAM_DEPTH * SLOT_BYTES) + warp * 1024 + lane * 32;   // IN_PROLONG only
 
   // Persistent warps: every warp pulls (strip, row segment) tasks from an atomic queue until it is
   // empty, so there is no wave quantisation and no CTA waits for its slowest warp.
@@ -405,19 +404,19 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     // row_cell[] / row_w[] of fine row r travel in the ring slot of row r; the coarse row index needed
     // when a copy is ISSUED (DEPTH rows ahead) comes from a lane-distributed table: lane l holds
     // row_cell[tab_base + l], looked up by shuffle and refilled every 32 rows (double buffered).
-    int cqx = 0, cqy = 0, prev_rq = -4, cbase = 0, tab = 0, tab_nxt = 0, tab_base = 0;
-    unsigned ox = 0, oy = 0;                     // byte offsets of this lane's two cells inside a staged coarse row
+    int cqx = 0, cqy = 0, cbase = 0, tab = 0, tab_nxt = 0, tab_base = 0;
+    int prev_rq = -4;
     double2 bot = make_double2(0.0, 0.0), top = bot;
+    unsigned ox = 0, oy = 0;                     // byte offsets of this lane's two cells inside a staged coarse row
+    double2 wcx, wcy;                            // this lane's column weights
     if (IN == IN_PROLONG) {
-        double2 wcx = bot, wcy = bot;
+        wcx = wcy = make_double2(0.0, 0.0);
         if (col_ok) {
             cqx = p.col_cell[cx];
             cqy = p.col_cell[cx + 1];
             wcx = p.col_w[cx];
             wcy = p.col_w[cx + 1];
         }
-        sts2(wc_addr, wcx);                       // this lane's column weights live in shared memory (register relief)
-        sts2(wc_addr + 16, wcy);
         tab_base = r_first;
         tab = p.row_cell[min(r_first + lane, N - 1)];
         tab_nxt = p.row_cell[min(r_first + 32 + lane, N - 1)];
@@ -457,8 +456,10 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
             // rows prefetched beyond the ones a task needs may map outside the local coarse slab: clamp (never used)
             const double *src = p.Uc + (ptrdiff_t)min(max(rq + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
             const bool ok0 = row_ok && c0 < p.Nc, ok1 = row_ok && c0 + 1 < p.Nc;
-            cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
-            cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
+            {
+                cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
+                cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
+            }
             if (lane == 0) {
                 const int rr = row_ok ? r : 0;
                 cp_async16(warp_ring + off + 1536, p.row_w + rr, row_ok);
@@ -477,33 +478,33 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         const int rq_first = __shfl_sync(0xffffffffu, tab, 0);
         // lower coarse row of the first cell: the only one that is not staged
         const double *c_lo = p.Uc + (ptrdiff_t)max(rq_first, p.uc_row0) * p.Nc;   // (clamped: only a warm-up row can ask for less)
+        double2 low = make_double2(0.0, 0.0);
         if (col_ok) {
-            const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
-            top.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
-            top.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
+            low.x = __dadd_rn(__dmul_rn(c_lo[cqx], wcx.x), __dmul_rn(c_lo[cqx + 1], wcx.y));
+            low.y = __dadd_rn(__dmul_rn(c_lo[cqy], wcy.x), __dmul_rn(c_lo[cqy + 1], wcy.y));
         }
-        prev_rq = rq_first - 1;                   // so that the first step shifts `top` down and loads the upper row
+        top = low;
+        prev_rq = rq_first - 1;                   // so that the first step shifts `top` down and takes the staged upper row
     }
     // Level 0 of the 1 node, U_f + P(U_c) (MG_solver_CPU.cpp:700 + :569), for the fine row staged in
-    // ring slot `so`.  Branch-free so that the compiler can interleave it with the sweeps of the
-    // previous row; lanes whose quotient left the safe range of the FMA division report `bad`.
+    // ring slot `so`; lanes whose quotient left the safe range of the FMA division report `bad`.
+    // The cell's two coarse rows, interpolated in x, are register rows that move under a warp-uniform branch when the
+    // cell changes (every other fine row of a nested ladder); the lane's column weights stay in registers.  (Measured
+    // against selects + weights in shared memory: -7 % -- the kernel is bound by issue slots and shared-memory bandwidth
+    // together, and under sustained load by the 1000 W power limit.)
     double2 x_next = make_double2(0.0, 0.0);
     double pvx = 0.0, pvy = 0.0, puf_x = 0.0, puf_y = 0.0;   // operands kept for the rare IEEE redo
     auto prolong_from_slot = [&](unsigned so) -> bool {
         const double2 uf = lds2(ring_base + so);
         const double2 wr = lds2(warp_ring + so + 1536);          // row_w[r]
         const int rq = lds_int(warp_ring + so + 1552);           // row_cell[r]
-        const bool changed = rq != prev_rq;                      // the cell moved up one coarse row
         const unsigned cs = warp_ring + so + 1024;
-        const double2 wcx = lds2(wc_addr), wcy = lds2(wc_addr + 16);
-        double2 ntop;
-        ntop.x = __dadd_rn(__dmul_rn(lds1(cs + ox), wcx.x), __dmul_rn(lds1(cs + ox + 8), wcx.y));
-        ntop.y = __dadd_rn(__dmul_rn(lds1(cs + oy), wcy.x), __dmul_rn(lds1(cs + oy + 8), wcy.y));
-        bot.x = changed ? top.x : bot.x;
-        bot.y = changed ? top.y : bot.y;
-        top.x = changed ? ntop.x : top.x;
-        top.y = changed ? ntop.y : top.y;
-        prev_rq = rq;
+        if (rq != prev_rq) {                                     // warp-uniform: the cell moved up one coarse row
+            bot = top;
+            top.x = __dadd_rn(__dmul_rn(lds1(cs + ox), wcx.x), __dmul_rn(lds1(cs + ox + 8), wcx.y));
+            top.y = __dadd_rn(__dmul_rn(lds1(cs + oy), wcy.x), __dmul_rn(lds1(cs + oy + 8), wcy.y));
+            prev_rq = rq;
+        }
         const double vx = __dadd_rn(__dmul_rn(bot.x, wr.x), __dmul_rn(top.x, wr.y));
         const double vy = __dadd_rn(__dmul_rn(bot.y, wr.x), __dmul_rn(top.y, wr.y));
         const double d = p.c_dx, y = p.inv_c_dx;
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         pvx = vx; pvy = vy; puf_x = uf.x; puf_y = uf.y;
         return col_ok && (div2_unsafe(vx) | div2_unsafe(vy));    // off-grid lanes compute -0 = c * 0 (never stored)
     };
-    auto prolong_redo = [&](bool bad) {                          // rare: IEEE divisions for the whole warp
+    auto prolong_redo = [&](bool bad) {             // rare: IEEE divisions for the whole warp
         if (__any_sync(0xffffffffu, bad)) {
             const double d = p.c_dx;
             x_next.x = __dadd_rn(puf_x, __ddiv_rn(__ddiv_rn(pvx, d), d));
@@ -563,10 +564,13 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 if (RES && lane == 0) cp_async16(warp_ring + slot_off + 1024, p.rrow + (r + STREAM_DEPTH - S - 2));
                 if (IN == IN_PROLONG) {
                     const int c0 = cbase + 2 * lane;
-                    const double *src = p.Uc + (ptrdiff_t)min(max(cell_of_row(r + STREAM_DEPTH) + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
+                    const int rq_iss = cell_of_row(r + STREAM_DEPTH);
+                    const double *src = p.Uc + (ptrdiff_t)min(max(rq_iss + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
                     const bool ok0 = c0 < p.Nc, ok1 = c0 + 1 < p.Nc;
-                    cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
-                    cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
+                    {
+                        cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
+                        cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
+                    }
                     if (lane == 0) {
                         cp_async16(warp_ring + slot_off + 1536, p.row_w + r + STREAM_DEPTH, true);
                         cp_async4(warp_ring + slot_off + 1552, p.row_cell + r + STREAM_DEPTH, true);
