@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(stream_smem);
     const unsigned warp_ring = smem0 + warp * (STREAM_DEPTH * SLOT_BYTES);
     const unsigned ring_base = warp_ring + lane * 16;
+    const unsigned coarse_dst = warp_ring + 1024 + lane * 8;    // IN_PROLONG: this lane's piece of the staged coarse row
 
   // Persistent warps: every warp pulls (strip, row segment) tasks from an atomic queue until it is
   // empty, so there is no wave quantisation and no CTA waits for its slowest warp.
@@ -451,15 +452,15 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
             cp_async16(warp_ring + off + 1024, ok ? (const void *)(p.rrow + fr_) : (const void *)p.F_valid, ok);
         }
         if (IN == IN_PROLONG) {
-            const int c0 = cbase + 2 * lane;
+            // lane l copies elements l and 32 + l of the 64 staged doubles: each copy instruction fills 256 contiguous
+            // bytes (interleaved 8-byte pieces at a 16-byte stride cost two extra shared-memory wavefronts per instruction)
+            const int c0 = cbase + lane;
             const bool row_ok = active && r <= N - 1;
             // rows prefetched beyond the ones a task needs may map outside the local coarse slab: clamp (never used)
             const double *src = p.Uc + (ptrdiff_t)min(max(rq + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
-            const bool ok0 = row_ok && c0 < p.Nc, ok1 = row_ok && c0 + 1 < p.Nc;
-            {
-                cp_async8(ring_base + off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
-                cp_async8(ring_base + off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
-            }
+            const bool ok0 = row_ok && c0 < p.Nc, ok1 = row_ok && c0 + 32 < p.Nc;
+            cp_async8(coarse_dst + off, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
+            cp_async8(coarse_dst + off + 256, ok1 ? (const void *)(src + 32) : (const void *)p.F_valid, ok1);
             if (lane == 0) {
                 const int rr = row_ok ? r : 0;
                 cp_async16(warp_ring + off + 1536, p.row_w + rr, row_ok);
@@ -563,14 +564,12 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
                 if (NF > 0) cp_async16(ring_base + slot_off + 512, Fp + (ptrdiff_t)(r + STREAM_DEPTH - 1) * ldn + cx);
                 if (RES && lane == 0) cp_async16(warp_ring + slot_off + 1024, p.rrow + (r + STREAM_DEPTH - S - 2));
                 if (IN == IN_PROLONG) {
-                    const int c0 = cbase + 2 * lane;
+                    const int c0 = cbase + lane;
                     const int rq_iss = cell_of_row(r + STREAM_DEPTH);
                     const double *src = p.Uc + (ptrdiff_t)min(max(rq_iss + 1, p.uc_row0), p.uc_row0 + p.uc_rows - 1) * p.Nc + c0;
-                    const bool ok0 = c0 < p.Nc, ok1 = c0 + 1 < p.Nc;
-                    {
-                        cp_async8(ring_base + slot_off + 1024, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
-                        cp_async8(ring_base + slot_off + 1032, ok1 ? (const void *)(src + 1) : (const void *)p.F_valid, ok1);
-                    }
+                    const bool ok0 = c0 < p.Nc, ok1 = c0 + 32 < p.Nc;
+                    cp_async8(coarse_dst + slot_off, ok0 ? (const void *)src : (const void *)p.F_valid, ok0);
+                    cp_async8(coarse_dst + slot_off + 256, ok1 ? (const void *)(src + 32) : (const void *)p.F_valid, ok1);
                     if (lane == 0) {
                         cp_async16(warp_ring + slot_off + 1536, p.row_w + r + STREAM_DEPTH, true);
                         cp_async4(warp_ring + slot_off + 1552, p.row_cell + r + STREAM_DEPTH, true);
