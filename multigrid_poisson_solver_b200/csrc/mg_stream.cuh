@@ -175,6 +175,15 @@ __device__ __forceinline__ bool div2_unsafe(double x)
     return (e - 220u > 1560u) && ((hi | (unsigned)__double2loint(x)) != 0u);
 }
 
+// Cheap superset of div2_unsafe(x) | div2_unsafe(y) for the common path (no zero exemption, one compare for both):
+// the caller evaluates the precise test only when some lane reports a suspect.
+__device__ __forceinline__ bool div2_suspect(double x, double y)
+{
+    const unsigned ax = ((unsigned)__double2hiint(x) & 0x7fffffffu) - (220u << 20);
+    const unsigned ay = ((unsigned)__double2hiint(y) & 0x7fffffffu) - (220u << 20);
+    return max(ax, ay) > (1561u << 20) - 1u;       // biased exponent outside [220, 1780]
+}
+
 // ---- end of a launch: the last CTA to drain the queue resets it and folds the per-task error
 // partials.  Thread t adds partials t, t+T, ... in that order, then the fixed shuffle tree and the
 // warps in order: the summation tree depends only on the task geometry and the CTA shape, never on
@@ -513,13 +522,17 @@ __global__ void __launch_bounds__(stream_shape(RES).warps * 32, stream_shape(RES
         x_next.x = __dadd_rn(uf.x, div_fast(qx, d, y));
         x_next.y = __dadd_rn(uf.y, div_fast(qy, d, y));
         pvx = vx; pvy = vy; puf_x = uf.x; puf_y = uf.y;
-        return col_ok && (div2_unsafe(vx) | div2_unsafe(vy));    // off-grid lanes compute -0 = c * 0 (never stored)
+        return div2_suspect(vx, vy);                             // (a superset of the unsafe lanes: zeros, off-grid lanes)
     };
-    auto prolong_redo = [&](bool bad) {             // rare: IEEE divisions for the whole warp
-        if (__any_sync(0xffffffffu, bad)) {
-            const double d = p.c_dx;
-            x_next.x = __dadd_rn(puf_x, __ddiv_rn(__ddiv_rn(pvx, d), d));
-            x_next.y = __dadd_rn(puf_y, __ddiv_rn(__ddiv_rn(pvy, d), d));
+    auto prolong_redo = [&](bool suspect) {                      // rare: IEEE divisions for the whole warp
+        if (__any_sync(0xffffffffu, suspect)) {
+            // the precise test: +0 is safe (every boundary column feeds it in), off-grid lanes compute -0 = c * 0 (never stored)
+            const bool bad = col_ok && (div2_unsafe(pvx) | div2_unsafe(pvy));
+            if (__any_sync(0xffffffffu, bad)) {
+                const double d = p.c_dx;
+                x_next.x = __dadd_rn(puf_x, __ddiv_rn(__ddiv_rn(pvx, d), d));
+                x_next.y = __dadd_rn(puf_y, __ddiv_rn(__ddiv_rn(pvy, d), d));
+            }
         }
     };
     if (IN == IN_PROLONG) {
