@@ -109,3 +109,34 @@ def test_smoothing_stress_matches_do_smoothing(mg, N, step):
     ref, eref = g.doSmoothing(N, 1.0, np.zeros(N * N), g.getSource(N), step)
     assert np.array_equal(U, ref)
     assert err.value == pytest.approx(eref, rel=1e-10)
+
+
+def test_split_launch_path_on_small_slabs():
+    """The edge + interior split of a slab pass (normally only from 32 M owned points on) forced on small slabs with
+    MG_SPLIT_MIN_POINTS=1 (read when the library is loaded, hence the subprocess): the edge launch with peer stores and
+    flags, then the interior launch adding its error sums -- same bits as the single-GPU run, V / trigger / W / restart cycles."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, tempfile
+import numpy as np
+import multigrid_poisson_solver_b200 as mg
+mg.init(0)
+cases = [(mg.cycles.v_cycle(1024, 8), 2, 256), (mg.cycles.v_cycle(1024, 8), 4, 256), (mg.cycles.v_cycle(1024, 8, step=-1), 3, 256),
+         (mg.cycles.w_cycle(1024, 8, levels=4, step=2, tol=1e-7), 2, 256), (mg.cycles.v_cycle(1024, 8, step=7, cycles=2), 2, 512)]
+for text, world, thr in cases:
+    f = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False); f.write(text); f.close()
+    one = mg.run_cycle_host(f.name, mg.RUN_FUSED | mg.RUN_QUIET)
+    emu = mg.run_cycle_dist_emulated(f.name, world, thr)
+    os.unlink(f.name)
+    assert np.array_equal(emu["U"], one["U"]), (world, thr)
+    assert [t["steps"] for t in emu["trace"]] == [t["steps"] for t in one["trace"]]
+    for a, b in zip(emu["trace"], one["trace"]):
+        if b["node"] != 0:
+            assert abs(a["err"] - b["err"]) <= 1e-10 * abs(b["err"]), (a, b)
+print("SPLIT_OK")
+'''
+    env = dict(os.environ, MG_SPLIT_MIN_POINTS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert r.returncode == 0 and "SPLIT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
