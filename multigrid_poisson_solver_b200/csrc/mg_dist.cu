@@ -2,10 +2,12 @@
 //
 // Fine levels are partitioned into contiguous row slabs, one per rank (one process per GPU); every
 // slab carries HALO extra rows on each side.  The halo rows of an array are refreshed WHEN THE ARRAY
-// IS PRODUCED and BY THE KERNEL THAT PRODUCES IT: the fused pass (k_strip) stores the rows a
-// neighbour keeps as its halo -- of the smoothed grid and of the restricted source -- straight into
-// the neighbour's slab through peer pointers (CUDA IPC over NVLink), while the rest of the same
-// launch sweeps the interior.  When the launch has drained, its last CTA publishes the pass number
+// IS PRODUCED and BY THE KERNEL THAT PRODUCES IT: the fused pass (k_stream<PEER> / k_strip) stores the
+// rows a neighbour keeps as its halo -- of the smoothed grid and of the restricted source -- straight
+// into the neighbour's slab through peer pointers (CUDA IPC over NVLink).  Large slabs are launched in
+// two parts: the thin row segments at both ends (peer stores, flags) first, then the interior with the
+// single-GPU kernel, so the halo rows cross NVLink while the interior is swept.  When the (edge) launch
+// has drained, its last CTA publishes the pass number
 // in a flag word of each neighbour (st.release.sys); the neighbour's stream waits for that value
 // (cuStreamWaitValue32, no SM, no host) in front of its next pass.  There is no communication kernel,
 // no send/recv group and no extra stream on the data path.
@@ -23,10 +25,14 @@
 // handle per rank (exchanged when the arena is created or grown, outside the timed region after the
 // first cycle) gives all peer pointers.
 //
-// The smoothing error is the all-reduced sum of the slabs' red-parity sums (one NCCL all-reduce per
-// batch of nodes; per sweep only in the trigger mode).  NCCL is otherwise used for the rendezvous
-// and for exchanging the IPC handles; it is bound at run time (dlopen of the libnccl.so.2 the host
-// program already loaded), so the library has no link-time NCCL dependency.
+// The smoothing error is the sum of the slabs' red-parity sums.  The sums stay on the device per batch
+// of nodes; one exchange over peer memory (every rank stores its partials into every rank's scalar
+// table and waits for the others' flag, the host adds in rank order: identical on all ranks) replaces
+// an all-reduce; error-trigger loops exchange two scalars per two-sweep pass.  NCCL is used for the
+// rendezvous, for exchanging the IPC handles and for host-side agreement on allocation success only; it
+// is bound at run time (dlopen of the libnccl.so.2 the host program already loaded), so the library
+// has no link-time NCCL dependency.  A rank that fails locally publishes an abort word: its peers come
+// back with an error instead of waiting (gather waits also time out).
 //
 //   EmuComm   all ranks live in this process on the current GPU: the same arenas, peer stores, flags
 //             and stream waits, with every rank's passes queued in rank order on one stream.  It
